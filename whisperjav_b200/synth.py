@@ -1,0 +1,184 @@
+"""Deterministic synthetic weights and audio (there are no checkpoints and no network on
+either box).
+
+``synth_weights`` fills the exact Whisper architecture (names follow the openai-whisper
+``state_dict``) with seeded values chosen so that greedy decoding is *non-degenerate*:
+attention is peaky enough that logits depend on the audio window, the tied embedding is
+spread so the argmax changes step to step, and the EOT row is boosted so sequences end
+at varied lengths.  ``speech_shaped_audio`` is the
+"Japanese-speech-shaped" generator of SURVEY.md section 8d.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict
+
+import numpy as np
+import torch
+
+
+@dataclass(frozen=True)
+class Dims:
+    """Whisper ``ModelDimensions`` (upstream whisper/model.py)."""
+    n_mels: int
+    n_audio_ctx: int
+    n_audio_state: int
+    n_audio_head: int
+    n_audio_layer: int
+    n_vocab: int
+    n_text_ctx: int
+    n_text_state: int
+    n_text_head: int
+    n_text_layer: int
+
+
+DIMS = {
+    "tiny": Dims(80, 1500, 384, 6, 4, 51865, 448, 384, 6, 4),
+    "base": Dims(80, 1500, 512, 8, 6, 51865, 448, 512, 8, 6),
+    "small": Dims(80, 1500, 768, 12, 12, 51865, 448, 768, 12, 12),
+    "medium": Dims(80, 1500, 1024, 16, 24, 51865, 448, 1024, 16, 24),
+    "large-v2": Dims(80, 1500, 1280, 20, 32, 51865, 448, 1280, 20, 32),
+    "large": Dims(80, 1500, 1280, 20, 32, 51865, 448, 1280, 20, 32),
+    "large-v3": Dims(128, 1500, 1280, 20, 32, 51866, 448, 1280, 20, 32),
+}
+
+EOT = 50257
+
+
+def _sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
+    inc = math.log(max_timescale) / (channels // 2 - 1)
+    inv = torch.exp(-inc * torch.arange(channels // 2))
+    t = torch.arange(length)[:, None] * inv[None, :]
+    return torch.cat([torch.sin(t), torch.cos(t)], dim=1)
+
+
+def synth_weights(dims: Dims, seed: int = 11, dtype=torch.float16, eot_boost: float = 1.5,
+                  logit_std: float = 3.0, attn_logit_std: float = 10.0, res_gain: float = None) -> Dict[str, torch.Tensor]:
+    """Seeded weights in openai-whisper ``state_dict`` naming.  Stored in ``dtype`` (fp16:
+    what the reference's ``fp16=True`` run holds after ``model.half()``)."""
+    g = torch.Generator().manual_seed(seed)
+    if res_gain is None:
+        res_gain = math.sqrt(32.0 / dims.n_text_layer)
+
+    def rn(*shape, std=1.0):
+        return (torch.randn(*shape, generator=g) * std).to(dtype)
+
+    w: Dict[str, torch.Tensor] = {}
+
+    def ln(prefix, n):
+        w[prefix + ".weight"] = (1.0 + 0.1 * torch.randn(n, generator=g)).to(dtype)
+        w[prefix + ".bias"] = rn(n, std=0.1)
+
+    def attn(prefix, n, n_head):
+        d = n // n_head
+        # q.k/sqrt(d) with unit-variance inputs has std  sq*sk*n*sqrt(d)/sqrt(d) = sq*sk*n
+        s_qk = math.sqrt(attn_logit_std / n)
+        w[prefix + ".query.weight"] = rn(n, n, std=s_qk)
+        w[prefix + ".query.bias"] = rn(n, std=0.1)
+        w[prefix + ".key.weight"] = rn(n, n, std=s_qk)
+        w[prefix + ".value.weight"] = rn(n, n, std=1.0 / math.sqrt(n))
+        w[prefix + ".value.bias"] = rn(n, std=0.1)
+        w[prefix + ".out.weight"] = rn(n, n, std=res_gain / math.sqrt(n))
+        w[prefix + ".out.bias"] = rn(n, std=0.05)
+
+    def mlp(prefix, n):
+        w[prefix + ".0.weight"] = rn(4 * n, n, std=1.0 / math.sqrt(n))
+        w[prefix + ".0.bias"] = rn(4 * n, std=0.1)
+        w[prefix + ".2.weight"] = rn(n, 4 * n, std=0.8 * res_gain / math.sqrt(4 * n))
+        w[prefix + ".2.bias"] = rn(n, std=0.05)
+
+    n = dims.n_audio_state
+    w["encoder.conv1.weight"] = rn(n, dims.n_mels, 3, std=1.0 / math.sqrt(dims.n_mels * 3))
+    w["encoder.conv1.bias"] = rn(n, std=0.1)
+    w["encoder.conv2.weight"] = rn(n, n, 3, std=1.5 / math.sqrt(n * 3))
+    w["encoder.conv2.bias"] = rn(n, std=0.1)
+    w["encoder.positional_embedding"] = _sinusoids(dims.n_audio_ctx, n).to(dtype)
+    for i in range(dims.n_audio_layer):
+        p = f"encoder.blocks.{i}"
+        ln(p + ".attn_ln", n)
+        attn(p + ".attn", n, dims.n_audio_head)
+        ln(p + ".mlp_ln", n)
+        mlp(p + ".mlp", n)
+    ln("encoder.ln_post", n)
+
+    n = dims.n_text_state
+    emb = torch.randn(dims.n_vocab, n, generator=g) * (logit_std / math.sqrt(n))
+    emb[EOT] *= eot_boost
+    w["decoder.token_embedding.weight"] = emb.to(dtype)
+    w["decoder.positional_embedding"] = rn(dims.n_text_ctx, n, std=0.5 * logit_std / math.sqrt(n))
+    for i in range(dims.n_text_layer):
+        p = f"decoder.blocks.{i}"
+        ln(p + ".attn_ln", n)
+        attn(p + ".attn", n, dims.n_text_head)
+        ln(p + ".cross_attn_ln", n)
+        attn(p + ".cross_attn", n, dims.n_text_head)
+        ln(p + ".mlp_ln", n)
+        mlp(p + ".mlp", n)
+    ln("decoder.ln", n)
+    return w
+
+
+# ------------------------------------------------------------------------------- audio
+def _resonator(x: np.ndarray, f: float, bw: float, sr: int) -> np.ndarray:
+    """Two-pole resonator (formant) applied with scipy.signal.lfilter."""
+    from scipy.signal import lfilter
+    r = math.exp(-math.pi * bw / sr)
+    theta = 2 * math.pi * f / sr
+    a = [1.0, -2 * r * math.cos(theta), r * r]
+    b = [1.0 - r]
+    return lfilter(b, a, x)
+
+
+def speech_shaped_audio(seconds: float, seed: int, sr: int = 16000, duty: float = 0.55) -> np.ndarray:
+    """"Japanese-speech-shaped" mono fp32 audio in [-1, 1]: harmonic
+    source on f0 in U(110, 320) Hz with slow contour, three formant resonators, mora-rate AM
+    6.5-8.5 Hz, 20 % unvoiced fricative morae, utterances 0.4-4 s separated by 0.15-2.5 s
+    pauses, pink-ish background noise at -35..-20 dBFS, peak -3 dBFS, int16-quantised."""
+    from scipy.signal import lfilter
+    rng = np.random.default_rng(seed)
+    n = int(round(seconds * sr))
+    out = np.zeros(n, dtype=np.float64)
+    t = 0
+    # background: white -> one-pole low-pass ~ pink-ish
+    bg = lfilter([0.05], [1.0, -0.95], rng.standard_normal(n))
+    bg *= 10 ** (rng.uniform(-35, -20) / 20) / (np.abs(bg).max() + 1e-9)
+    pause_lo, pause_hi = 0.15, 2.5
+    # scale pause range so that the speech duty is roughly ``duty``
+    while t < n:
+        pause = math.exp(rng.uniform(math.log(pause_lo), math.log(pause_hi))) * (1 - duty) / 0.45
+        t += int(pause * sr)
+        if t >= n:
+            break
+        dur = rng.uniform(0.4, 4.0)
+        m = min(int(dur * sr), n - t)
+        if m < 160:
+            break
+        tt = np.arange(m) / sr
+        f0 = rng.uniform(110, 320)
+        contour = f0 * (1 + 0.15 * np.sin(2 * math.pi * rng.uniform(0.3, 1.2) * tt + rng.uniform(0, 6.28)))
+        phase = 2 * math.pi * np.cumsum(contour) / sr
+        src = np.zeros(m)
+        for h in range(1, 25):
+            if h * f0 * 1.15 > sr / 2:
+                break
+            src += np.sin(h * phase) / h
+        mora = rng.uniform(6.5, 8.5)
+        am = 0.55 + 0.45 * np.sin(2 * math.pi * mora * tt + rng.uniform(0, 6.28))
+        # unvoiced morae: replace 20 % of mora periods with high-passed noise
+        mora_idx = (tt * mora).astype(int)
+        unv = rng.random(mora_idx.max() + 1) < 0.2
+        noise = rng.standard_normal(m)
+        noise = noise - lfilter([0.3], [1.0, -0.7], noise)  # crude high-pass
+        sig = np.where(unv[mora_idx], 0.5 * noise, src)
+        v = np.zeros(m)
+        for (lo, hi), bw in zip(((300, 900), (900, 2500), (2500, 3500)), (90, 120, 160)):
+            v += _resonator(sig, rng.uniform(lo, hi), bw, sr)
+        env = np.minimum(1.0, np.minimum(tt, tt[::-1]) / 0.03)
+        out[t:t + m] += v * am * env
+        t += m
+    out /= (np.abs(out).max() + 1e-9)
+    out = out * 10 ** (-3 / 20) * 0.9 + bg
+    out = np.clip(out, -1.0, 1.0)
+    q = np.round(out * 32767.0).astype(np.int16)  # the WAV hand-off is PCM16
+    return (q.astype(np.float32) / 32768.0).astype(np.float32)
