@@ -1,0 +1,131 @@
+/* libwjb200.so -- C-ABI of the B200-native WhisperJAV ASR hot path.
+ *
+ * The reference (meizhong986/WhisperJAV @ f7862f7) has no FFI of its own: its hot path is Python
+ * calling third-party packages.  Every entry point below therefore cites the *reference call site*
+ * whose arithmetic it replaces (paths relative to the reference repo root) and, in brackets, the
+ * upstream function that call site reaches (openai-whisper 20250625 @ c0d2f62).  The Python side
+ * of the boundary (whisperjav_b200/) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions: all pointers are device pointers unless marked host; `stream` is a cudaStream_t
+ * passed as void*; no function allocates device memory (callers supply workspaces sized by the
+ * *_workspace_bytes functions); every function returns 0 on success and a non-zero status on error,
+ * with a message available from wjb_last_error(); nothing throws across the ABI.
+ */
+#ifndef WJB200_H_
+#define WJB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WJB_ABI_VERSION 1
+
+/* Whisper ModelDimensions [whisper/model.py::ModelDimensions]; the model name that selects them
+ * arrives at whisperjav/modules/whisper_pro_asr.py:45,182 (`whisper.load_model(model_name)`). */
+typedef struct wjb_dims {
+    int32_t n_mels, n_audio_ctx, n_audio_state, n_audio_head, n_audio_layer;
+    int32_t n_vocab, n_text_ctx, n_text_state, n_text_head, n_text_layer;
+} wjb_dims;
+
+typedef struct wjb_model wjb_model; /* opaque */
+
+int wjb_abi_version(void);
+const char* wjb_last_error(void); /* host string, thread-local */
+
+/* ---- weights: one packed device blob --------------------------------------------------------
+ * Replaces `whisper.load_model(name, device)` (whisper_pro_asr.py:182) as far as placement goes:
+ * the caller converts a state_dict into this layout (whisperjav_b200/weights.py). */
+size_t wjb_weights_bytes(const wjb_dims* dims);
+int wjb_weight_count(const wjb_dims* dims);
+/* index -> name (copied into name_buf), byte offset, byte size, dtype (0 = fp16, 1 = fp32) */
+int wjb_weight_info(const wjb_dims* dims, int index, char* name_buf, int name_buf_len, size_t* offset, size_t* nbytes,
+                    int* dtype);
+int wjb_model_create(const wjb_dims* dims, const void* weights_blob, wjb_model** out);
+void wjb_model_destroy(wjb_model* m);
+
+/* ---- log-mel ------------------------------------------------------------------------------
+ * Replaces `log_mel_spectrogram(audio, n_mels, padding=N_SAMPLES)` + `pad_or_trim` inside
+ * `whisper_model.transcribe` (whisper_pro_asr.py:433) [whisper/audio.py], and
+ * `WhisperProcessor(audio)` at modules/subtitle_pipeline/generators/anime_whisper.py:256-263 and
+ * `WhisperFeatureExtractor` at modules/speech_segmentation/backends/whisperseg.py:376-380.
+ *   audio      fp32 [n_clips][audio_stride]; n_samples (device int32 [n_clips]) valid samples each
+ *   filters    fp32 [n_mels][201] Slaney mel filterbank
+ *   out        fp16; time_major=1: [n_clips][out_rows][n_mels] with frame t at row row0+t
+ *                    time_major=0: [n_clips][n_mels][n_frames]        (upstream layout)
+ *   frames t >= n_samples/160 are literal zeros (pad_or_trim semantics); reflect_total = 0 means the
+ *   signal is followed by >= 200 zeros (transcribe's 30 s padding), else the padded length at which the
+ *   right edge reflects (480000 for the HF feature extractor).
+ *   workspace: wjb_logmel_workspace_bytes(n_clips, n_mels) bytes. */
+size_t wjb_logmel_workspace_bytes(int n_clips, int n_mels);
+int wjb_logmel_f16(const float* audio, int64_t audio_stride, const int32_t* n_samples, int n_clips, int n_mels,
+                   const float* filters, void* out, int time_major, int64_t out_clip_stride, int row0, int n_frames,
+                   int reflect_total, void* workspace, void* stream);
+
+/* ---- encoder ------------------------------------------------------------------------------
+ * Replaces `model.encoder(mel)` reached from whisper_pro_asr.py:433 [whisper/model.py::AudioEncoder.forward]
+ * and `model.generate()`'s encoder pass at generators/anime_whisper.py:279.
+ *   mel_tm  fp16 [B][2*n_audio_ctx + 2][n_mels], time-major, rows 0 and 2*n_audio_ctx+1 zero (conv padding)
+ *   out     fp16 [B][n_audio_ctx][n_audio_state] */
+size_t wjb_encoder_workspace_bytes(const wjb_model* m, int batch);
+int wjb_encoder_forward(wjb_model* m, const void* mel_tm, int batch, void* out, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ---- cross-attention K/V projection (once per window) ---------------------------------------
+ * Replaces the first-step `cross_attn.key/value(xa)` Linear calls cached by the KV hooks
+ * [whisper/model.py::MultiHeadAttention.forward, whisper/decoding.py::PyTorchInference].
+ *   kv_out fp16 [n_text_layer][B][2*n_text_head][n_audio_ctx][64]  (K heads, then V heads) */
+size_t wjb_cross_kv_bytes(const wjb_model* m, int batch);
+int wjb_cross_kv(wjb_model* m, const void* enc_out, int batch, void* kv_out, void* stream);
+
+/* ---- greedy decode (persistent on device, one host read-back per run) ------------------------
+ * Replaces `DecodingTask.run` / `_main_loop` [whisper/decoding.py] reached through
+ * `decode_with_fallback` in `whisper_model.transcribe` (whisper_pro_asr.py:433) and HF
+ * `model.generate(do_sample=False, num_beams=1)` (generators/anime_whisper.py:269-279). */
+typedef struct wjb_decode_opts {
+    int32_t n_initial;     /* forced prefix length (sot sequence [+ prompt]) = sample_begin */
+    int32_t sot_index;     /* position of <|startoftranscript|> in the prefix */
+    int32_t sample_len;    /* max sampled tokens (n_text_ctx / 2) */
+    int32_t eot, no_speech, no_timestamps, timestamp_begin;
+    int32_t suppress_blank, blank_token;
+    int32_t apply_timestamp_rules;        /* 0 when without_timestamps */
+    int32_t max_initial_timestamp_index;  /* -1 = none */
+    int32_t tokens_stride;                /* ints per row of `tokens` (>= n_initial + sample_len + 1) */
+    int32_t check_every;                  /* host polls the done counter every this many steps (0 = 8) */
+} wjb_decode_opts;
+
+size_t wjb_decode_workspace_bytes(const wjb_model* m, int batch);
+/*   cross_kv       from wjb_cross_kv
+ *   suppress_mask  uint8 [n_vocab] (1 = suppressed) or NULL         [SuppressTokens]
+ *   tokens         int32 [B][tokens_stride]; caller fills the first n_initial entries of every row
+ *   sum_logprob    fp32 [B] (out), no_speech_prob fp32 [B] (out), out_len int32 [B] (out: sampled tokens before EOT)
+ *   steps_run      host int (out, may be NULL): decoder steps executed */
+int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_decode_opts* opts,
+                      const uint8_t* suppress_mask, int32_t* tokens, float* sum_logprob, float* no_speech_prob,
+                      int32_t* out_len, void* workspace, size_t workspace_bytes, int* steps_run, void* stream);
+
+/* ---- building blocks exposed for parity tests and profiling ---------------------------------- */
+/* out[r][n] = epilogue(sum_k A[r][k] W[n][k]); flags: 1 = GELU (exact erf).  All fp16, fp32 accumulate. */
+int wjb_gemm_f16(const void* A, int64_t a_row_stride, int64_t a_batch_stride, int rows_per_batch, int n_batch, int K,
+                 const void* W, int N, int ldw, const void* bias, const void* residual, void* out, int64_t out_row_stride,
+                 int64_t out_batch_stride, int flags, int block_n, void* stream);
+int wjb_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int n, void* stream);
+int wjb_attention_encoder_f16(const void* qkv, void* out, int batch, int T, int n_head, void* stream);
+/* single decoder step pieces */
+int wjb_attention_cross_f16(const void* q, const void* kv, void* out, int batch, int n_head, int T, void* stream);
+
+/* ---- voice-activity gate ----------------------------------------------------------------------
+ * Replaces the per-window model calls inside `get_speech_timestamps(tensor, jit_model)` at
+ * modules/speech_segmentation/backends/silero.py:269-273 (and silero_v6.py:205-210; the per-hop
+ * `TenVad.process` loop at backends/ten.py:232-239): audio -> per-window speech probability.
+ * Architecture and weight layout: see whisperjav_b200/vad.py.  probs fp32 [n_clips][n_windows]. */
+size_t wjb_vad_weights_bytes(void);
+int wjb_vad_forward(const float* audio, int64_t audio_stride, const int32_t* n_samples, int n_clips, const void* weights,
+                    float* probs, int n_windows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WJB200_H_ */

@@ -194,7 +194,7 @@ def _attention(q, k, v, n_head, causal: bool, r):
         t_k = k.shape[2]
         mask = torch.full((n_ctx, t_k), float("-inf")).triu_(1 + t_k - n_ctx)
         qk = qk + mask
-    w = torch.softmax(qk.float(), dim=-1)
+    w = r(torch.softmax(qk.float(), dim=-1))  # non-SDPA branch: softmax(qk.float()).to(q.dtype)
     out = w @ v
     return r(out.permute(0, 2, 1, 3).flatten(start_dim=2))
 
@@ -210,7 +210,7 @@ def encoder_forward(weights: Dict[str, torch.Tensor], dims: ModelDimensions, mel
     pos = weights.get("encoder.positional_embedding")
     if pos is None:
         pos = sinusoids(dims.n_audio_ctx, dims.n_audio_state)
-    x = r(x + r(pos.float()))
+    x = r(x + pos.float())  # fp16 x + fp32 buffer -> fp32 sum, .to(x.dtype)
     layers = []
     for i in range(dims.n_audio_layer):
         p = f"encoder.blocks.{i}"
@@ -277,7 +277,7 @@ def decoder_forward(weights, dims: ModelDimensions, tokens: torch.Tensor, xa: to
         x = r(x + _linear(h, weights, p + ".mlp.2", r))
     x = _layer_norm(x, weights, "decoder.ln", r)
     state.offset = offset + T
-    return (x @ emb.t()).float()
+    return r(x @ emb.t()).float()  # fp16 matmul output, then .float()
 
 
 # ----------------------------------------------------------------------------- tokenizer.py

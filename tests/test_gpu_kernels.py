@@ -1,0 +1,193 @@
+"""Kernel-level parity on the GPU, through the C-ABI (ctypes), against plain torch fp32 math on the
+same fp16 inputs.  Tolerances are written next to each assertion."""
+import ctypes as C
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from whisperjav_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def r16(t):
+    return t.half().float()
+
+
+def gemm(lib, A, W, bias=None, res=None, flags=0, block_n=0, rows_per_batch=None, n_batch=1, a_row_stride=None,
+         a_batch_stride=0, K=None, out=None):
+    N = W.shape[0]
+    K = K or W.shape[1]
+    rows = rows_per_batch or A.shape[0]
+    if out is None:
+        out = torch.empty(n_batch * rows, N, dtype=torch.float16, device=DEV)
+    _lib.check(lib.wjb_gemm_f16(_lib.ptr(A), a_row_stride or K, a_batch_stride, rows, n_batch, K, _lib.ptr(W), N, W.shape[1],
+                                _lib.ptr(bias), _lib.ptr(res), _lib.ptr(out), N, rows * N, flags, block_n, _lib.stream_ptr()), "gemm")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 256), (128, 256, 256, 256), (256, 512, 128, 128), (1000, 1280, 1280, 0),
+                                      (64, 1280, 1280, 64), (3, 384, 384, 64), (130, 51866, 384, 0), (4096, 3840, 1280, 256)])
+def test_gemm_plain(lib, diag_dir, M, N, K, bn):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    A = (torch.randn(M, K, generator=g) * 0.5).half().to(DEV)
+    W = (torch.randn(N, K, generator=g) * 0.05).half().to(DEV)
+    if N % 64:
+        outbuf = torch.zeros(M, (N + 63) // 64 * 64, dtype=torch.float16, device=DEV)
+        _lib.check(lib.wjb_gemm_f16(_lib.ptr(A), K, 0, M, 1, K, _lib.ptr(W), N, K, None, None, _lib.ptr(outbuf), outbuf.shape[1], 0, 0, bn,
+                                    _lib.stream_ptr()), "gemm")
+        torch.cuda.synchronize()
+        out = outbuf[:, :N]
+    else:
+        out = gemm(lib, A, W, block_n=bn)
+    ref = A.float() @ W.float().t()
+    err = (out.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    if not err <= 2e-3 * scale + 1e-3:
+        np.save(diag_dir / f"gemm_{M}_{N}_{K}_out.npy", out[:256, :512].float().cpu().numpy())
+        np.save(diag_dir / f"gemm_{M}_{N}_{K}_ref.npy", ref[:256, :512].cpu().numpy())
+    # fp16 output rounding: <= 2^-11 relative of the value plus accumulation-order noise
+    assert err <= 2e-3 * scale + 1e-3, (err, scale)
+
+
+def test_gemm_epilogues(lib):
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 777, 1280, 640
+    A = (torch.randn(M, K, generator=g)).half().to(DEV)
+    W = (torch.randn(N, K, generator=g) * 0.04).half().to(DEV)
+    bias = (torch.randn(N, generator=g) * 0.3).half().to(DEV)
+    res = (torch.randn(M, N, generator=g)).half().to(DEV)
+    lin = r16(A.float() @ W.float().t() + bias.float())
+    out = gemm(lib, A, W, bias=bias)
+    assert (out.float() - lin).abs().max().item() <= 4e-3
+    out = gemm(lib, A, W, bias=bias, flags=1)
+    ref = r16(torch.nn.functional.gelu(lin))
+    assert (out.float() - ref).abs().max().item() <= 4e-3
+    out = gemm(lib, A, W, bias=bias, res=res)
+    ref = r16(lin + res.float())
+    assert (out.float() - ref).abs().max().item() <= 8e-3
+    # in-place residual (out aliases residual), as the transformer blocks use it
+    x = res.clone()
+    gemm(lib, A, W, bias=bias, res=x, out=x)
+    assert (x.float() - ref).abs().max().item() <= 8e-3
+
+
+@pytest.mark.parametrize("C_,stride,T_out", [(128, 1, 3000), (80, 1, 3000), (384, 2, 1500), (1280, 2, 1500)])
+def test_gemm_conv_im2col_free(lib, C_, stride, T_out):
+    """k=3 convolution as a GEMM over overlapping rows of the channels-last padded input."""
+    B, N = 2, 256
+    T_in = T_out * stride
+    g = torch.Generator().manual_seed(C_)
+    x = (torch.randn(B, C_, T_in, generator=g)).half()
+    w = (torch.randn(N, C_, 3, generator=g) * (1.0 / (3 * C_) ** 0.5)).half()
+    bias = (torch.randn(N, generator=g) * 0.1).half()
+    xpad = torch.zeros(B, T_in + 2, C_, dtype=torch.float16)
+    xpad[:, 1:-1] = x.permute(0, 2, 1)
+    wk = w.permute(0, 2, 1).reshape(N, 3 * C_).contiguous()
+    out = torch.empty(B * T_out, N, dtype=torch.float16, device=DEV)
+    xp, wkd, bd = xpad.to(DEV), wk.to(DEV), bias.to(DEV)
+    _lib.check(lib.wjb_gemm_f16(_lib.ptr(xp), stride * C_, (T_in + 2) * C_, T_out, B, 3 * C_, _lib.ptr(wkd), N, 3 * C_, _lib.ptr(bd), None,
+                                _lib.ptr(out), N, T_out * N, 0, 0, _lib.stream_ptr()), "conv gemm")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv1d(x.float(), w.float(), bias.float(), stride=stride, padding=1).permute(0, 2, 1).reshape(B * T_out, N)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err <= 4e-3 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("rows,n", [(5, 384), (1000, 1280), (64, 1280), (33, 512)])
+def test_layernorm(lib, rows, n):
+    g = torch.Generator().manual_seed(rows)
+    x = (torch.randn(rows, n, generator=g) * 3 + 0.5).half().to(DEV)
+    ga = (1 + 0.1 * torch.randn(n, generator=g)).half().to(DEV)
+    be = (0.1 * torch.randn(n, generator=g)).half().to(DEV)
+    out = torch.empty_like(x)
+    _lib.check(lib.wjb_layernorm_f16(_lib.ptr(x), _lib.ptr(ga), _lib.ptr(be), _lib.ptr(out), rows, n, _lib.stream_ptr()), "ln")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (n,), ga.float(), be.float(), 1e-5)
+    assert (out.float() - ref).abs().max().item() <= 4e-3  # one fp16 ulp at |y| < 4
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 1500, 6), (2, 1500, 20), (1, 256, 2), (3, 200, 1)])
+def test_attention_encoder(lib, diag_dir, B, T, H):
+    n = 64 * H
+    g = torch.Generator().manual_seed(T + H)
+    qkv = (torch.randn(B * T, 3 * n, generator=g) * 1.2).half().to(DEV)
+    out = torch.zeros(B * T, n, dtype=torch.float16, device=DEV)
+    _lib.check(lib.wjb_attention_encoder_f16(_lib.ptr(qkv), _lib.ptr(out), B, T, H, _lib.stream_ptr()), "attn")
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v
+    ref = ref.permute(0, 2, 1, 3).reshape(B * T, n)
+    err = (out.float() - ref).abs().max().item()
+    if not err <= 6e-3:
+        np.save(diag_dir / f"attn_{B}_{T}_{H}_out.npy", out[:256].float().cpu().numpy())
+        np.save(diag_dir / f"attn_{B}_{T}_{H}_ref.npy", ref[:256].cpu().numpy())
+    # fp16 P and fp16 output: a few 1e-3 absolute on O(1) values
+    assert err <= 6e-3, err
+
+
+@pytest.mark.parametrize("B,H,T", [(2, 6, 1500), (64, 20, 1500), (3, 1, 100)])
+def test_attention_cross(lib, B, H, T):
+    n = 64 * H
+    g = torch.Generator().manual_seed(B + T)
+    q = (torch.randn(B, n, generator=g) * 1.5).half().to(DEV)
+    kv = (torch.randn(B, 2 * H, T, 64, generator=g)).half().to(DEV)
+    out = torch.empty(B, n, dtype=torch.float16, device=DEV)
+    _lib.check(lib.wjb_attention_cross_f16(_lib.ptr(q), _lib.ptr(kv), _lib.ptr(out), B, H, T, _lib.stream_ptr()), "cross")
+    torch.cuda.synchronize()
+    qh = q.float().view(B, H, 1, 64)
+    k, v = kv[:, :H].float(), kv[:, H:].float()
+    w = r16(torch.softmax(qh @ k.transpose(-1, -2) * 0.125, -1))
+    ref = (w @ v).reshape(B, n)
+    assert (out.float() - ref).abs().max().item() <= 3e-3
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_logmel_vs_torch(lib, diag_dir, n_mels):
+    """Fused STFT+mel+log kernel vs torch.stft in fp32 (tolerance from north_star: 1e-3 abs)."""
+    from whisperjav_b200.model import slaney_mel_filters
+    from whisperjav_b200.synth import speech_shaped_audio
+    clips = [speech_shaped_audio(s, 50 + i) for i, s in enumerate([30.0, 7.3, 0.5, 29.99])]
+    clips.append(np.zeros(16000, np.float32))
+    B = len(clips)
+    S = max(len(c) for c in clips)
+    audio = torch.zeros(B, S)
+    for i, c in enumerate(clips):
+        audio[i, : len(c)] = torch.from_numpy(c)
+    ns = torch.tensor([len(c) for c in clips], dtype=torch.int32)
+    filt = torch.from_numpy(slaney_mel_filters(n_mels))
+    for layout in ("mel", "time"):
+        nf = 3000
+        a_d, ns_d, f_d = audio.to(DEV), ns.to(DEV), filt.to(DEV)
+        ws = torch.zeros(lib.wjb_logmel_workspace_bytes(B, n_mels), dtype=torch.uint8, device=DEV)
+        if layout == "mel":
+            out = torch.full((B, n_mels, nf), 7.0, dtype=torch.float16, device=DEV)
+            args = (0, n_mels * nf, 0)
+        else:
+            out = torch.zeros(B, nf + 2, n_mels, dtype=torch.float16, device=DEV)
+            args = (1, (nf + 2) * n_mels, 1)
+        _lib.check(lib.wjb_logmel_f16(_lib.ptr(a_d), S, _lib.ptr(ns_d), B, n_mels, _lib.ptr(f_d), _lib.ptr(out), args[0], args[1], args[2], nf, 0,
+                                      _lib.ptr(ws), _lib.stream_ptr()), "logmel")
+        torch.cuda.synchronize()
+        got = out.float().cpu()
+        if layout == "time":
+            assert got[:, 0].abs().max() == 0 and got[:, -1].abs().max() == 0
+            got = got[:, 1:-1].permute(0, 2, 1)
+        for i, c in enumerate(clips):
+            x = torch.nn.functional.pad(torch.from_numpy(c), (0, 480000))
+            st = torch.stft(x, 400, 160, window=torch.hann_window(400), return_complex=True)
+            mag = st[..., :-1].abs() ** 2
+            ls = torch.clamp(filt @ mag, min=1e-10).log10()
+            ls = (torch.maximum(ls, ls.max() - 8.0) + 4.0) / 4.0
+            cf = len(c) // 160
+            ref = torch.zeros(n_mels, nf)
+            ref[:, : min(cf, nf)] = ls[:, : min(cf, nf)]
+            err = (got[i] - ref).abs().max().item()
+            if err > 1e-3:
+                np.save(diag_dir / f"mel_{n_mels}_{layout}_{i}_got.npy", got[i].numpy())
+                np.save(diag_dir / f"mel_{n_mels}_{layout}_{i}_ref.npy", ref.numpy())
+            assert err <= 1e-3, (layout, i, err)

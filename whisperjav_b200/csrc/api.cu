@@ -1,0 +1,608 @@
+// extern "C" surface of libwjb200.so (see include/wjb200.h) plus the host-side orchestration of the
+// encoder forward, the cross-K/V projection and the CUDA-graph-replayed greedy decode loop.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/wjb200.h"
+#include "kernels.h"
+
+namespace wjb {
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+
+int set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+tensor_map_encode_fn get_tensor_map_encoder() {
+    static tensor_map_encode_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tensor_map_encode_fn>(p);
+    }
+    return fn;
+}
+
+int sample_init();
+
+static int init_kernels() {
+    static bool done = false;
+    if (done) return 0;
+    if (int e = gemm_init()) return e;
+    if (int e = attn_init()) return e;
+    if (int e = sample_init()) return e;
+    done = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------ weight blob layout
+struct Entry {
+    std::string name;
+    size_t offset, bytes;
+    int dtype;  // 0 fp16, 1 fp32
+};
+struct Layout {
+    std::vector<Entry> e;
+    size_t total = 0;
+    void add(const std::string& name, size_t elems, int dtype = 0) {
+        const size_t bytes = elems * (dtype ? 4 : 2);
+        e.push_back({name, total, bytes, dtype});
+        total += (bytes + 255) & ~size_t(255);
+    }
+    size_t off(const std::string& name) const {
+        for (auto& x : e)
+            if (x.name == name) return x.offset;
+        return (size_t)-1;
+    }
+};
+
+static Layout build_layout(const wjb_dims& d) {
+    Layout L;
+    const size_t n = d.n_audio_state, C = d.n_mels;
+    L.add("enc.conv1.w", n * 3 * C);
+    L.add("enc.conv1.b", n);
+    L.add("enc.conv2.w", n * 3 * n);
+    L.add("enc.conv2.b", n);
+    L.add("enc.pos", (size_t)d.n_audio_ctx * n, 1);
+    for (int i = 0; i < d.n_audio_layer; ++i) {
+        const std::string p = "enc." + std::to_string(i) + ".";
+        L.add(p + "ln1.g", n);
+        L.add(p + "ln1.b", n);
+        L.add(p + "qkv.w", 3 * n * n);
+        L.add(p + "qkv.b", 3 * n);
+        L.add(p + "out.w", n * n);
+        L.add(p + "out.b", n);
+        L.add(p + "ln2.g", n);
+        L.add(p + "ln2.b", n);
+        L.add(p + "fc1.w", 4 * n * n);
+        L.add(p + "fc1.b", 4 * n);
+        L.add(p + "fc2.w", 4 * n * n);
+        L.add(p + "fc2.b", n);
+    }
+    L.add("enc.ln_post.g", n);
+    L.add("enc.ln_post.b", n);
+    const size_t t = d.n_text_state;
+    L.add("dec.emb", (size_t)d.n_vocab * t);
+    L.add("dec.pos", (size_t)d.n_text_ctx * t);
+    for (int i = 0; i < d.n_text_layer; ++i) {
+        const std::string p = "dec." + std::to_string(i) + ".";
+        L.add(p + "ln1.g", t);
+        L.add(p + "ln1.b", t);
+        L.add(p + "qkv.w", 3 * t * t);
+        L.add(p + "qkv.b", 3 * t);
+        L.add(p + "out.w", t * t);
+        L.add(p + "out.b", t);
+        L.add(p + "ln2.g", t);
+        L.add(p + "ln2.b", t);
+        L.add(p + "cq.w", t * t);
+        L.add(p + "cq.b", t);
+        L.add(p + "ckv.w", 2 * t * t);
+        L.add(p + "ckv.b", 2 * t);
+        L.add(p + "cout.w", t * t);
+        L.add(p + "cout.b", t);
+        L.add(p + "ln3.g", t);
+        L.add(p + "ln3.b", t);
+        L.add(p + "fc1.w", 4 * t * t);
+        L.add(p + "fc1.b", 4 * t);
+        L.add(p + "fc2.w", 4 * t * t);
+        L.add(p + "fc2.b", t);
+    }
+    L.add("dec.ln.g", t);
+    L.add("dec.ln.b", t);
+    return L;
+}
+
+}  // namespace wjb
+
+using namespace wjb;
+
+struct wjb_model {
+    wjb_dims d;
+    const uint8_t* blob;
+    Layout L;
+    // decode graph cache
+    cudaGraphExec_t graph = nullptr;
+    const void* g_kv = nullptr;
+    void* g_ws = nullptr;
+    int g_B = 0;
+    wjb_decode_opts g_opts;
+    const void* g_mask = nullptr;
+    int32_t* g_tokens = nullptr;
+    float* g_slp = nullptr;
+    float* g_nsp = nullptr;
+    int32_t* g_len = nullptr;
+    int* h_done = nullptr;  // pinned
+    const __half* h16(const std::string& name) const { return reinterpret_cast<const __half*>(blob + L.off(name)); }
+    const float* f32(const std::string& name) const { return reinterpret_cast<const float*>(blob + L.off(name)); }
+};
+
+static bool dims_ok(const wjb_dims* d) {
+    return d && d->n_audio_state % 64 == 0 && d->n_text_state % 64 == 0 && d->n_audio_state == d->n_audio_head * 64 &&
+           d->n_text_state == d->n_text_head * 64 && d->n_mels % 8 == 0 && d->n_mels <= 128 && d->n_text_ctx <= 448 &&
+           d->n_audio_ctx <= 1536 && d->n_audio_state <= 2048 && d->n_text_state <= 2048;
+}
+
+extern "C" {
+
+int wjb_abi_version(void) { return WJB_ABI_VERSION; }
+const char* wjb_last_error(void) { return g_err; }
+
+size_t wjb_weights_bytes(const wjb_dims* dims) {
+    if (!dims_ok(dims)) return 0;
+    return build_layout(*dims).total;
+}
+int wjb_weight_count(const wjb_dims* dims) {
+    if (!dims_ok(dims)) return 0;
+    return (int)build_layout(*dims).e.size();
+}
+int wjb_weight_info(const wjb_dims* dims, int index, char* name_buf, int name_buf_len, size_t* offset, size_t* nbytes, int* dtype) {
+    if (!dims_ok(dims)) return set_error("unsupported dims (head dim must be 64)");
+    Layout L = build_layout(*dims);
+    if (index < 0 || index >= (int)L.e.size()) return set_error("weight index out of range");
+    const Entry& e = L.e[index];
+    if (name_buf && name_buf_len > 0) {
+        strncpy(name_buf, e.name.c_str(), name_buf_len - 1);
+        name_buf[name_buf_len - 1] = 0;
+    }
+    if (offset) *offset = e.offset;
+    if (nbytes) *nbytes = e.bytes;
+    if (dtype) *dtype = e.dtype;
+    return 0;
+}
+
+int wjb_model_create(const wjb_dims* dims, const void* weights_blob, wjb_model** out) {
+    if (!dims_ok(dims)) return set_error("unsupported dims (need head dim 64, n_mels<=128, ctx<=448/1536)");
+    if (!weights_blob || !out) return set_error("null argument");
+    if (int e = init_kernels()) return e;
+    wjb_model* m = new wjb_model();
+    m->d = *dims;
+    m->blob = reinterpret_cast<const uint8_t*>(weights_blob);
+    m->L = build_layout(*dims);
+    if (cudaHostAlloc(&m->h_done, sizeof(int) * 4, cudaHostAllocDefault) != cudaSuccess) {
+        delete m;
+        return set_error("cudaHostAlloc failed");
+    }
+    *out = m;
+    return 0;
+}
+
+void wjb_model_destroy(wjb_model* m) {
+    if (!m) return;
+    if (m->graph) cudaGraphExecDestroy(m->graph);
+    if (m->h_done) cudaFreeHost(m->h_done);
+    delete m;
+}
+
+// ------------------------------------------------------------------ log-mel
+size_t wjb_logmel_workspace_bytes(int n_clips, int n_mels) { return (size_t)n_clips * 4 + 256 + (size_t)n_mels * 8 + 256; }
+
+int wjb_logmel_f16(const float* audio, int64_t audio_stride, const int32_t* n_samples, int n_clips, int n_mels, const float* filters,
+                   void* out, int time_major, int64_t out_clip_stride, int row0, int n_frames, int reflect_total, void* workspace,
+                   void* stream) {
+    if (!audio || !n_samples || !filters || !out || !workspace) return set_error("logmel: null argument");
+    LogmelArgs a;
+    a.audio = audio;
+    a.audio_stride = audio_stride;
+    a.n_samples = n_samples;
+    a.n_clips = n_clips;
+    a.n_mels = n_mels;
+    a.filters = filters;
+    a.out = reinterpret_cast<__half*>(out);
+    a.time_major = time_major;
+    a.out_clip_stride = out_clip_stride;
+    a.row0 = row0;
+    a.n_frames = n_frames;
+    a.reflect_total = reflect_total;
+    a.clip_max = reinterpret_cast<float*>(workspace);
+    a.mel_range = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (((size_t)n_clips * 4 + 255) & ~size_t(255)));
+    return launch_logmel(a, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ encoder
+static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct EncWs {
+    __half *c1, *x, *h, *qkv, *mlp;
+    size_t total;
+};
+static EncWs enc_ws(const wjb_dims& d, int B, uint8_t* base) {
+    EncWs w;
+    const size_t n = d.n_audio_state, T = d.n_audio_ctx, T2 = 2 * T + 2;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        uint8_t* p = base ? base + off : nullptr;
+        off += al(bytes);
+        return reinterpret_cast<__half*>(p);
+    };
+    w.c1 = take((size_t)B * T2 * n * 2);
+    w.x = take((size_t)B * T * n * 2);
+    w.h = take((size_t)B * T * n * 2);
+    w.qkv = take((size_t)B * T * 3 * n * 2);
+    w.mlp = take((size_t)B * T * 4 * n * 2);
+    w.total = off;
+    return w;
+}
+
+size_t wjb_encoder_workspace_bytes(const wjb_model* m, int batch) {
+    if (!m || batch <= 0) return 0;
+    return enc_ws(m->d, batch, nullptr).total;
+}
+
+int wjb_encoder_forward(wjb_model* m, const void* mel_tm, int batch, void* out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!m || !mel_tm || !out || !workspace) return set_error("encoder: null argument");
+    const wjb_dims& d = m->d;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = batch, n = d.n_audio_state, T = d.n_audio_ctx, T2 = 2 * T + 2, C = d.n_mels, H = d.n_audio_head;
+    EncWs w = enc_ws(d, B, reinterpret_cast<uint8_t*>(workspace));
+    if (w.total > workspace_bytes) return set_error("encoder: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    // zero pad rows 0 and 2T+1 of the conv1 output
+    for (int r = 0; r < 2; ++r) {
+        cudaError_t e = cudaMemset2DAsync(w.c1 + (size_t)(r ? (T2 - 1) : 0) * n, (size_t)T2 * n * 2, 0, (size_t)n * 2, B, s);
+        if (e != cudaSuccess) return set_error("encoder memset: %s", cudaGetErrorString(e));
+    }
+    GemmArgs g;
+    // conv1: [B][2T+2][C] -> rows 1..2T of c1, GELU
+    g = GemmArgs();
+    g.A = reinterpret_cast<const __half*>(mel_tm);
+    g.a_row_stride = C;
+    g.a_batch_stride = (long long)T2 * C;
+    g.rows_per_batch = 2 * T;
+    g.n_batch = B;
+    g.K = 3 * C;
+    g.W = m->h16("enc.conv1.w");
+    g.N = n;
+    g.ldw = 3 * C;
+    g.bias = m->h16("enc.conv1.b");
+    g.out = w.c1 + n;
+    g.out_row_stride = n;
+    g.out_batch_stride = (long long)T2 * n;
+    g.flags = GEMM_GELU;
+    if (int e = launch_gemm(g, s)) return e;
+    // conv2 (stride 2) + GELU + positional embedding -> x [B][T][n]
+    g = GemmArgs();
+    g.A = w.c1;
+    g.a_row_stride = 2 * n;
+    g.a_batch_stride = (long long)T2 * n;
+    g.rows_per_batch = T;
+    g.n_batch = B;
+    g.K = 3 * n;
+    g.W = m->h16("enc.conv2.w");
+    g.N = n;
+    g.ldw = 3 * n;
+    g.bias = m->h16("enc.conv2.b");
+    g.pos = m->f32("enc.pos");
+    g.out = w.x;
+    g.out_row_stride = n;
+    g.out_batch_stride = (long long)T * n;
+    g.flags = GEMM_GELU;
+    if (int e = launch_gemm(g, s)) return e;
+
+    const int M = B * T;
+    auto linear = [&](const __half* A, int K, const __half* W, const __half* bias, const __half* res, __half* o, int N, int flags) {
+        GemmArgs q;
+        q.A = A;
+        q.a_row_stride = K;
+        q.rows_per_batch = M;
+        q.n_batch = 1;
+        q.K = K;
+        q.W = W;
+        q.N = N;
+        q.ldw = K;
+        q.bias = bias;
+        q.residual = res;
+        q.out = o;
+        q.out_row_stride = N;
+        q.flags = flags;
+        return launch_gemm(q, s);
+    };
+    for (int i = 0; i < d.n_audio_layer; ++i) {
+        const std::string p = "enc." + std::to_string(i) + ".";
+        if (int e = launch_layernorm(w.x, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"), w.h, M, n, s)) return e;
+        if (int e = linear(w.h, n, m->h16(p + "qkv.w"), m->h16(p + "qkv.b"), nullptr, w.qkv, 3 * n, 0)) return e;
+        if (int e = launch_attn_encoder(w.qkv, w.h, B, T, H, s)) return e;
+        if (int e = linear(w.h, n, m->h16(p + "out.w"), m->h16(p + "out.b"), w.x, w.x, n, 0)) return e;
+        if (int e = launch_layernorm(w.x, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"), w.h, M, n, s)) return e;
+        if (int e = linear(w.h, n, m->h16(p + "fc1.w"), m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, GEMM_GELU)) return e;
+        if (int e = linear(w.mlp, 4 * n, m->h16(p + "fc2.w"), m->h16(p + "fc2.b"), w.x, w.x, n, 0)) return e;
+    }
+    return launch_layernorm(w.x, m->h16("enc.ln_post.g"), m->h16("enc.ln_post.b"), reinterpret_cast<__half*>(out), M, n, s);
+}
+
+// ------------------------------------------------------------------ cross K/V
+size_t wjb_cross_kv_bytes(const wjb_model* m, int batch) {
+    if (!m) return 0;
+    return (size_t)m->d.n_text_layer * batch * 2 * m->d.n_text_head * m->d.n_audio_ctx * 64 * 2;
+}
+
+int wjb_cross_kv(wjb_model* m, const void* enc_out, int batch, void* kv_out, void* stream) {
+    if (!m || !enc_out || !kv_out) return set_error("cross_kv: null argument");
+    const wjb_dims& d = m->d;
+    if (d.n_audio_state != d.n_text_state) return set_error("cross_kv: audio/text widths differ");
+    const int n = d.n_text_state, T = d.n_audio_ctx, H = d.n_text_head;
+    const size_t per_layer = (size_t)batch * 2 * H * T * 64;
+    for (int i = 0; i < d.n_text_layer; ++i) {
+        const std::string p = "dec." + std::to_string(i) + ".";
+        GemmArgs g;
+        g.A = reinterpret_cast<const __half*>(enc_out);
+        g.a_row_stride = n;
+        g.a_batch_stride = (long long)T * n;
+        g.rows_per_batch = T;
+        g.n_batch = batch;
+        g.K = n;
+        g.W = m->h16(p + "ckv.w");
+        g.N = 2 * n;
+        g.ldw = n;
+        g.bias = m->h16(p + "ckv.b");
+        g.out = reinterpret_cast<__half*>(kv_out) + (size_t)i * per_layer;
+        g.flags = GEMM_HEADSPLIT;
+        g.hs_T = T;
+        g.hs_H = 2 * H;
+        if (int e = launch_gemm(g, (cudaStream_t)stream)) return e;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ greedy decode
+struct DecWs {
+    __half *x, *h, *qkv, *q, *a, *mlp, *logits, *self_kv;
+    DecodeCtl* ctl;
+    unsigned char* done;
+    int logits_stride;
+    size_t total;
+};
+static DecWs dec_ws(const wjb_dims& d, int B, uint8_t* base) {
+    DecWs w;
+    const size_t n = d.n_text_state;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        uint8_t* p = base ? base + off : nullptr;
+        off += al(bytes);
+        return p;
+    };
+    w.logits_stride = (d.n_vocab + 63) & ~63;
+    w.x = (__half*)take((size_t)B * n * 2);
+    w.h = (__half*)take((size_t)B * n * 2);
+    w.qkv = (__half*)take((size_t)B * 3 * n * 2);
+    w.q = (__half*)take((size_t)B * n * 2);
+    w.a = (__half*)take((size_t)B * n * 2);
+    w.mlp = (__half*)take((size_t)B * 4 * n * 2);
+    w.logits = (__half*)take((size_t)B * w.logits_stride * 2);
+    w.self_kv = (__half*)take((size_t)d.n_text_layer * B * 2 * d.n_text_head * d.n_text_ctx * 64 * 2);
+    w.ctl = (DecodeCtl*)take(sizeof(DecodeCtl));
+    w.done = (unsigned char*)take((size_t)B);
+    w.total = off;
+    return w;
+}
+
+size_t wjb_decode_workspace_bytes(const wjb_model* m, int batch) {
+    if (!m || batch <= 0) return 0;
+    return dec_ws(m->d, batch, nullptr).total;
+}
+
+static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B, const wjb_decode_opts& o,
+                       const uint8_t* suppress_mask, int32_t* tokens, float* slp, float* nsp, int32_t* out_len, cudaStream_t s) {
+    const wjb_dims& d = m->d;
+    const int n = d.n_text_state, H = d.n_text_head, T = d.n_audio_ctx;
+    auto linear = [&](const __half* A, int K, const __half* W, int ldw, const __half* bias, const __half* res, __half* out, int N,
+                      long long out_stride, int flags) {
+        GemmArgs q;
+        q.A = A;
+        q.a_row_stride = K;
+        q.rows_per_batch = B;
+        q.n_batch = 1;
+        q.K = K;
+        q.W = W;
+        q.N = N;
+        q.ldw = ldw;
+        q.bias = bias;
+        q.residual = res;
+        q.out = out;
+        q.out_row_stride = out_stride;
+        q.flags = flags;
+        q.block_n = 64;
+        return launch_gemm(q, s);
+    };
+    if (int e = launch_embed(tokens, o.tokens_stride, m->h16("dec.emb"), m->h16("dec.pos"), w.x, w.ctl, B, n, s)) return e;
+    const size_t self_per_layer = (size_t)B * 2 * H * d.n_text_ctx * 64;
+    const size_t cross_per_layer = (size_t)B * 2 * H * T * 64;
+    for (int i = 0; i < d.n_text_layer; ++i) {
+        const std::string p = "dec." + std::to_string(i) + ".";
+        if (int e = launch_layernorm(w.x, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"), w.h, B, n, s)) return e;
+        if (int e = linear(w.h, n, m->h16(p + "qkv.w"), n, m->h16(p + "qkv.b"), nullptr, w.qkv, 3 * n, 3 * n, 0)) return e;
+        if (int e = launch_attn_dec_self(w.qkv, w.self_kv + i * self_per_layer, w.a, &w.ctl->step, w.done, B, H, d.n_text_ctx, s)) return e;
+        if (int e = linear(w.a, n, m->h16(p + "out.w"), n, m->h16(p + "out.b"), w.x, w.x, n, n, 0)) return e;
+        if (int e = launch_layernorm(w.x, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"), w.h, B, n, s)) return e;
+        if (int e = linear(w.h, n, m->h16(p + "cq.w"), n, m->h16(p + "cq.b"), nullptr, w.q, n, n, 0)) return e;
+        if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv) + i * cross_per_layer, w.a, w.done, B, H, T, s))
+            return e;
+        if (int e = linear(w.a, n, m->h16(p + "cout.w"), n, m->h16(p + "cout.b"), w.x, w.x, n, n, 0)) return e;
+        if (int e = launch_layernorm(w.x, m->h16(p + "ln3.g"), m->h16(p + "ln3.b"), w.h, B, n, s)) return e;
+        if (int e = linear(w.h, n, m->h16(p + "fc1.w"), n, m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, 4 * n, GEMM_GELU)) return e;
+        if (int e = linear(w.mlp, 4 * n, m->h16(p + "fc2.w"), 4 * n, m->h16(p + "fc2.b"), w.x, w.x, n, n, 0)) return e;
+    }
+    if (int e = launch_layernorm(w.x, m->h16("dec.ln.g"), m->h16("dec.ln.b"), w.h, B, n, s)) return e;
+    if (int e = linear(w.h, n, m->h16("dec.emb"), n, nullptr, nullptr, w.logits, d.n_vocab, w.logits_stride, 0)) return e;
+    DecodeParams p;
+    p.B = B;
+    p.n_vocab = d.n_vocab;
+    p.logits_stride = w.logits_stride;
+    p.eot = o.eot;
+    p.no_speech = o.no_speech;
+    p.no_timestamps = o.no_timestamps;
+    p.timestamp_begin = o.timestamp_begin;
+    p.suppress_blank = o.suppress_blank;
+    p.blank_token = o.blank_token;
+    p.apply_timestamp_rules = o.apply_timestamp_rules;
+    p.max_initial_timestamp_index = o.max_initial_timestamp_index;
+    p.n_ctx = d.n_text_ctx;
+    p.tokens_stride = o.tokens_stride;
+    return launch_sample(w.logits, suppress_mask, tokens, nullptr, slp, nsp, out_len, w.done, w.ctl, p, s);
+}
+
+int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_decode_opts* opts, const uint8_t* suppress_mask,
+                      int32_t* tokens, float* sum_logprob, float* no_speech_prob, int32_t* out_len, void* workspace,
+                      size_t workspace_bytes, int* steps_run, void* stream) {
+    if (!m || !cross_kv || !opts || !tokens || !sum_logprob || !no_speech_prob || !out_len || !workspace)
+        return set_error("decode: null argument");
+    const wjb_dims& d = m->d;
+    cudaStream_t s = (cudaStream_t)stream;
+    const wjb_decode_opts& o = *opts;
+    if (o.n_initial < 1 || o.sample_len < 1) return set_error("decode: bad n_initial/sample_len");
+    const int total_steps = o.n_initial - 1 + o.sample_len;
+    if (total_steps > d.n_text_ctx) return set_error("decode: n_initial + sample_len exceeds n_text_ctx");
+    if (o.tokens_stride < o.n_initial + o.sample_len) return set_error("decode: tokens_stride too small");
+    DecWs w = dec_ws(d, batch, reinterpret_cast<uint8_t*>(workspace));
+    if (w.total > workspace_bytes) return set_error("decode: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+
+    // reset per-run state
+    DecodeCtl h_ctl;
+    h_ctl.step = 0;
+    h_ctl.n_initial = o.n_initial;
+    h_ctl.sot_index = o.sot_index;
+    h_ctl.max_steps = o.sample_len;
+    h_ctl.n_done = 0;
+    cudaError_t ce;
+    if ((ce = cudaMemcpyAsync(w.ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+        return set_error("decode ctl copy: %s", cudaGetErrorString(ce));
+    cudaMemsetAsync(w.done, 0, batch, s);
+    cudaMemsetAsync(sum_logprob, 0, sizeof(float) * batch, s);
+    cudaMemsetAsync(no_speech_prob, 0, sizeof(float) * batch, s);
+    cudaMemsetAsync(out_len, 0, sizeof(int32_t) * batch, s);
+    // h_ctl lives on this stack frame: make sure the copy has been consumed before we return
+    const bool use_graph = getenv("WJB_NO_GRAPH") == nullptr;
+    if (use_graph) {
+        const bool hit = m->graph && m->g_kv == cross_kv && m->g_ws == workspace && m->g_B == batch && m->g_mask == suppress_mask &&
+                         m->g_tokens == tokens && m->g_slp == sum_logprob && m->g_nsp == no_speech_prob && m->g_len == out_len &&
+                         memcmp(&m->g_opts, &o, sizeof(o)) == 0;
+        if (!hit) {
+            if (m->graph) {
+                cudaGraphExecDestroy(m->graph);
+                m->graph = nullptr;
+            }
+            cudaStreamSynchronize(s);
+            cudaGraph_t graph = nullptr;
+            if ((ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
+                return set_error("decode: begin capture: %s", cudaGetErrorString(ce));
+            int e = decode_step(m, w, cross_kv, batch, o, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, s);
+            ce = cudaStreamEndCapture(s, &graph);
+            if (e) {
+                if (graph) cudaGraphDestroy(graph);
+                return e;
+            }
+            if (ce != cudaSuccess) return set_error("decode: end capture: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&m->graph, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return set_error("decode: graph instantiate: %s", cudaGetErrorString(ce));
+            m->g_kv = cross_kv;
+            m->g_ws = workspace;
+            m->g_B = batch;
+            m->g_mask = suppress_mask;
+            m->g_tokens = tokens;
+            m->g_slp = sum_logprob;
+            m->g_nsp = no_speech_prob;
+            m->g_len = out_len;
+            m->g_opts = o;
+        }
+    }
+    const int check_every = o.check_every > 0 ? o.check_every : 8;
+    int step = 0;
+    for (; step < total_steps; ++step) {
+        if (use_graph) {
+            if ((ce = cudaGraphLaunch(m->graph, s)) != cudaSuccess) return set_error("decode: graph launch: %s", cudaGetErrorString(ce));
+        } else {
+            if (int e = decode_step(m, w, cross_kv, batch, o, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, s)) return e;
+        }
+        if ((step + 1) % check_every == 0 && step + 1 >= o.n_initial) {
+            cudaMemcpyAsync(m->h_done, &w.ctl->n_done, sizeof(int), cudaMemcpyDeviceToHost, s);
+            if ((ce = cudaStreamSynchronize(s)) != cudaSuccess) return set_error("decode: sync: %s", cudaGetErrorString(ce));
+            if (*m->h_done >= batch) {
+                ++step;
+                break;
+            }
+        }
+    }
+    if ((ce = cudaStreamSynchronize(s)) != cudaSuccess) return set_error("decode: final sync: %s", cudaGetErrorString(ce));
+    if (steps_run) *steps_run = step;
+    return 0;
+}
+
+// ------------------------------------------------------------------ building blocks
+int wjb_gemm_f16(const void* A, int64_t a_row_stride, int64_t a_batch_stride, int rows_per_batch, int n_batch, int K, const void* W,
+                 int N, int ldw, const void* bias, const void* residual, void* out, int64_t out_row_stride, int64_t out_batch_stride,
+                 int flags, int block_n, void* stream) {
+    GemmArgs g;
+    g.A = (const __half*)A;
+    g.a_row_stride = a_row_stride;
+    g.a_batch_stride = a_batch_stride;
+    g.rows_per_batch = rows_per_batch;
+    g.n_batch = n_batch;
+    g.K = K;
+    g.W = (const __half*)W;
+    g.N = N;
+    g.ldw = ldw;
+    g.bias = (const __half*)bias;
+    g.residual = (const __half*)residual;
+    g.out = (__half*)out;
+    g.out_row_stride = out_row_stride;
+    g.out_batch_stride = out_batch_stride;
+    g.flags = flags & GEMM_GELU;
+    g.block_n = block_n;
+    return launch_gemm(g, (cudaStream_t)stream);
+}
+
+int wjb_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int n, void* stream) {
+    return launch_layernorm((const __half*)x, (const __half*)gamma, (const __half*)beta, (__half*)out, rows, n, (cudaStream_t)stream);
+}
+
+int wjb_attention_encoder_f16(const void* qkv, void* out, int batch, int T, int n_head, void* stream) {
+    if (int e = init_kernels()) return e;
+    return launch_attn_encoder((const __half*)qkv, (__half*)out, batch, T, n_head, (cudaStream_t)stream);
+}
+
+int wjb_attention_cross_f16(const void* q, const void* kv, void* out, int batch, int n_head, int T, void* stream) {
+    return launch_attn_dec_cross((const __half*)q, (const __half*)kv, (__half*)out, nullptr, batch, n_head, T, (cudaStream_t)stream);
+}
+
+}  // extern "C"

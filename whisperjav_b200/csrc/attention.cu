@@ -1,0 +1,454 @@
+// Attention kernels.
+//
+//  * attn_encoder_kernel: non-causal flash attention for the Whisper encoder (T = 1500, d = 64),
+//    tcgen05 for both matmuls.  One CTA = 128 query rows of one (batch, head); S = Q K^T lands in
+//    TMEM, four softmax warps (thread == query row == TMEM lane) read it back with tcgen05.ld, write
+//    fp16 P into a SWIZZLE_128B K-major smem tile, and P V runs as a second UMMA with V consumed
+//    MN-major straight from the TMA tile (no transpose).  The running output is kept in registers
+//    (O = O * alpha + PV).  Two CTAs are co-resident per SM (256 TMEM columns, ~97 KB smem each) so
+//    one CTA's exp phase overlaps the other's MMAs.  Replaces F.scaled_dot_product_attention in
+//    openai-whisper model.py::MultiHeadAttention.qkv_attention.
+//  * attn_dec_self_kernel / attn_dec_cross_kernel: single-query decode attention against the HBM
+//    KV cache / the per-window cross K,V; pure streaming, HBM-bound (cross: 384 KB per (b, head)).
+#include "kernels.h"
+
+namespace wjb {
+
+// ============================================================================ encoder
+constexpr int kAttnThreads = 192;
+constexpr int kQTile = 128, kKVTile = 128, kHeadDim = 64;
+constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB
+constexpr int kAttnSmem = 1024 + kTileBytes /*Q*/ + 2 * kTileBytes /*K*/ + kTileBytes /*V*/ + 2 * kTileBytes /*P*/ + 256;
+constexpr int kAttnTmemCols = 256;  // S: [0,128), O partial: [128,192)
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int T, int n_state) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + kTileBytes;       // 2 stages
+    uint8_t* sV = sK + 2 * kTileBytes;
+    uint8_t* sP = sV + kTileBytes;       // 2 k-blocks of [128 rows][64 keys]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileBytes);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;   // [2]
+    uint64_t* k_empty = bars + 3;  // [2]
+    uint64_t* v_full = bars + 5;
+    uint64_t* v_empty = bars + 6;
+    uint64_t* s_full = bars + 7;
+    uint64_t* p_full = bars + 8;
+    uint64_t* o_full = bars + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kQTile, h = blockIdx.y, b = blockIdx.z;
+    const int nkv = (T + kKVTile - 1) / kKVTile;
+
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+        }
+        mbar_init(v_full, 1);
+        mbar_init(v_empty, 1);
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 128);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        if (lane == 0) tma_prefetch_desc(&tmQKV);
+        tmem_alloc<kAttnTmemCols>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, kTileBytes);
+            tma_load_3d(sQ, &tmQKV, q_full, h * kHeadDim, q0, b);
+            for (int j = 0; j < nkv; ++j) {
+                const int st = j & 1;
+                mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&k_full[st], kTileBytes);
+                tma_load_3d(sK + st * kTileBytes, &tmQKV, &k_full[st], n_state + h * kHeadDim, j * kKVTile, b);
+                mbar_wait(v_empty, (j & 1) ^ 1);
+                mbar_arrive_expect_tx(v_full, kTileBytes);
+                tma_load_3d(sV, &tmQKV, v_full, 2 * n_state + h * kHeadDim, j * kKVTile, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);  // S = Q K^T, both K-major
+            constexpr uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);   // O = P V, V is MN-major
+            mbar_wait(q_full, 0);
+            const uint64_t dq = make_smem_desc(smem_u32(sQ), 16, 1024, kLayoutSW128);
+            for (int j = 0; j < nkv; ++j) {
+                const int st = j & 1;
+                mbar_wait(&k_full[st], (j >> 1) & 1);
+                tc_fence_after();
+                const uint64_t dk = make_smem_desc(smem_u32(sK + st * kTileBytes), 16, 1024, kLayoutSW128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                umma_commit(s_full);
+                umma_commit(&k_empty[st]);
+                mbar_wait(p_full, j & 1);
+                mbar_wait(v_full, j & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    // A: P k-block (k / 4), 32 B per 16 keys inside the 128 B row.  B: V rows 16*k.. (128 B per key row).
+                    const uint64_t dp = make_smem_desc(smem_u32(sP + (k >> 2) * kTileBytes) + (k & 3) * 32, 16, 1024, kLayoutSW128);
+                    const uint64_t dv = make_smem_desc(smem_u32(sV) + k * 16 * 128, 1024, 1024, kLayoutSW128);
+                    umma_f16(tmem_O, dp, dv, idesc_o, k != 0);
+                }
+                umma_commit(o_full);
+                umma_commit(v_empty);
+            }
+        }
+    } else {
+        // ===================== softmax warps: thread == query row =====================
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_off = uint32_t(quad * 32) << 16;
+        const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+        float m = -INFINITY, l = 0.f;
+        float O[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) O[i] = 0.f;
+
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            if (j > 0) {
+                mbar_wait(o_full, (j - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_O + lane_off + c * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(r[i]);
+                }
+            }
+            const int kvalid = T - j * kKVTile;  // keys >= kvalid are padding
+            // pass 1: row max
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_S + lane_off + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float s = __uint_as_float(r[i]);
+                    if (c * 32 + i < kvalid) mx = fmaxf(mx, s);
+                }
+            }
+            const float m_new = fmaxf(m, mx);
+            const float alpha = exp2f((m - m_new) * sl2);  // m = -inf on the first block -> 0
+            l *= alpha;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) O[i] *= alpha;
+            m = m_new;
+            const float mb = m_new * sl2;
+            // pass 2: p = exp2(s*sl2 - m*sl2) -> fp16 -> swizzled smem
+            float lsum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_S + lane_off + c * 32, r);
+                tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float p0 = exp2f(fmaf(__uint_as_float(r[2 * i]), sl2, -mb));
+                    float p1 = exp2f(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mb));
+                    if (c * 32 + 2 * i >= kvalid) p0 = 0.f;
+                    if (c * 32 + 2 * i + 1 >= kvalid) p1 = 0.f;
+                    lsum += p0 + p1;
+                    __half2 hp = __floats2half2_rn(p0, p1);
+                    packed[i] = *reinterpret_cast<uint32_t*>(&hp);
+                }
+                // keys [c*32, c*32+32) -> k-block c/2, 16-byte chunks (c&1)*4 .. +4 of this row
+                uint8_t* prow = sP + (c >> 1) * kTileBytes + row * 128;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(prow + chunk * 16) =
+                        make_uint4(packed[q4 * 4], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
+                }
+            }
+            l += lsum;
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        mbar_wait(o_full, (nkv - 1) & 1);
+        tc_fence_after();
+        const float inv_l = 1.0f / l;
+        const bool row_ok = q0 + row < T;
+        __half* orow = out + ((long long)b * T + q0 + row) * n_state + h * kHeadDim;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_O + lane_off + c * 32, r);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = q4 * 8 + 2 * i;
+                        oh[i] = __floats2half2_rn((O[c * 32 + idx] + __uint_as_float(r[idx])) * inv_l,
+                                                  (O[c * 32 + idx + 1] + __uint_as_float(r[idx + 1])) * inv_l);
+                    }
+                    *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<kAttnTmemCols>(tmem_base);
+    }
+}
+
+int attn_init() {
+    cudaError_t e = cudaFuncSetAttribute(attn_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) return set_error("attn attr: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int launch_attn_encoder(const __half* qkv, __half* out, int B, int T, int H, cudaStream_t s) {
+    const int n = H * kHeadDim;
+    auto fn = get_tensor_map_encoder();
+    if (!fn) return set_error("cuTensorMapEncodeTiled unavailable");
+    CUtensorMap tm;
+    uint64_t dims[3] = {(uint64_t)3 * n, (uint64_t)T, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)3 * n * 2, (uint64_t)T * 3 * n * 2};
+    uint32_t box[3] = {64, 128, 1};
+    uint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(qkv), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("attn tensor map encode failed (%d)", (int)r);
+    dim3 grid((T + kQTile - 1) / kQTile, H, B);
+    attn_encoder_kernel<<<grid, kAttnThreads, kAttnSmem, s>>>(tm, out, T, n);
+    WJB_CHECK_LAUNCH("attn_encoder");
+    return 0;
+}
+
+// ============================================================================ decoder self-attention
+// One warp per (b, head).  kv_cache [B][2H][n_ctx][64]: K heads 0..H-1, V heads H..2H-1.
+__global__ void __launch_bounds__(32) attn_dec_self_kernel(const __half* __restrict__ qkv, __half* __restrict__ kv_cache,
+                                                           __half* __restrict__ out, const int* __restrict__ step_ptr,
+                                                           const unsigned char* __restrict__ done, int H, int n_ctx) {
+    const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+    if (done && done[b]) return;
+    const int pos = *step_ptr;
+    const int n = H * 64;
+    __shared__ float probs[448];
+    const __half* row = qkv + (long long)b * 3 * n;
+    __half* kc = kv_cache + ((long long)(b * 2 * H + h) * n_ctx) * 64;
+    __half* vc = kv_cache + ((long long)(b * 2 * H + H + h) * n_ctx) * 64;
+    // append this token's k, v
+    reinterpret_cast<__half2*>(kc + (long long)pos * 64)[lane] = reinterpret_cast<const __half2*>(row + n + h * 64)[lane];
+    reinterpret_cast<__half2*>(vc + (long long)pos * 64)[lane] = reinterpret_cast<const __half2*>(row + 2 * n + h * 64)[lane];
+    __syncwarp();
+    float q[64];
+    {
+        const uint4* qp = reinterpret_cast<const uint4*>(row + h * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint4 u = qp[i];
+            const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h2[j]);
+                q[i * 8 + 2 * j] = f.x;
+                q[i * 8 + 2 * j + 1] = f.y;
+            }
+        }
+    }
+    float mx = -INFINITY;
+    for (int p = lane; p <= pos; p += 32) {
+        const uint4* kp = reinterpret_cast<const uint4*>(kc + (long long)p * 64);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint4 u = kp[i];
+            const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h2[j]);
+                s = fmaf(q[i * 8 + 2 * j], f.x, s);
+                s = fmaf(q[i * 8 + 2 * j + 1], f.y, s);
+            }
+        }
+        s *= 0.125f;
+        probs[p] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int p = lane; p <= pos; p += 32) {
+        const float e = __expf(probs[p] - mx);
+        probs[p] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    for (int p = 0; p <= pos; ++p) {
+        const float w = round_f16(probs[p] * inv);
+        float2 v = __half22float2(reinterpret_cast<const __half2*>(vc + (long long)p * 64)[lane]);
+        o0 = fmaf(w, v.x, o0);
+        o1 = fmaf(w, v.y, o1);
+    }
+    reinterpret_cast<__half2*>(out + (long long)b * n + h * 64)[lane] = __floats2half2_rn(o0, o1);
+}
+
+int launch_attn_dec_self(const __half* qkv, __half* kv_cache, __half* out, const int* step, const unsigned char* done, int B, int H,
+                         int n_ctx, cudaStream_t s) {
+    if (n_ctx > 448) return set_error("attn_dec_self: n_ctx %d > 448", n_ctx);
+    dim3 grid(H, B);
+    attn_dec_self_kernel<<<grid, 32, 0, s>>>(qkv, kv_cache, out, step, done, H, n_ctx);
+    WJB_CHECK_LAUNCH("attn_dec_self");
+    return 0;
+}
+
+// ============================================================================ decoder cross-attention
+// One CTA (128 threads) per (b, head); K and V are [T][64] fp16, streamed once each.
+constexpr int kCrossThreads = 128;
+constexpr int kCrossMaxT = 1536;
+
+__global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
+                                                                        __half* __restrict__ out,
+                                                                        const unsigned char* __restrict__ done, int H, int T) {
+    const int h = blockIdx.x, b = blockIdx.y;
+    if (done && done[b]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = H * 64;
+    __shared__ float sc[kCrossMaxT];
+    __shared__ float red[8];
+    __shared__ float osum[4][64];
+    const uint4* K = reinterpret_cast<const uint4*>(kv + ((long long)(b * 2 * H + h) * T) * 64);
+    const uint4* V = reinterpret_cast<const uint4*>(kv + ((long long)(b * 2 * H + H + h) * T) * 64);
+    const int chunk = tid & 7;   // which 16-byte (8 dims) slice of the 64-dim row
+    const int slot = tid >> 3;   // key slot 0..15 within an iteration
+    float qf[8];
+    {
+        uint4 u = reinterpret_cast<const uint4*>(q + (long long)b * n + h * 64)[chunk];
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = __half22float2(h2[j]);
+            qf[2 * j] = f.x;
+            qf[2 * j + 1] = f.y;
+        }
+    }
+    // ---- scores
+    for (int t0 = 0; t0 < T; t0 += 64) {
+        uint4 u[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int t = t0 + r * 16 + slot;
+            u[r] = (t < T) ? __ldg(K + (long long)t * 8 + chunk) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&u[r]);
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h2[j]);
+                s = fmaf(qf[2 * j], f.x, s);
+                s = fmaf(qf[2 * j + 1], f.y, s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            const int t = t0 + r * 16 + slot;
+            if (chunk == 0 && t < T) sc[t] = s * 0.125f;
+        }
+    }
+    __syncthreads();
+    // ---- softmax over T scores
+    float mx = -INFINITY;
+    for (int t = tid; t < T; t += kCrossThreads) mx = fmaxf(mx, sc[t]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    float sum = 0.f;
+    for (int t = tid; t < T; t += kCrossThreads) {
+        const float e = __expf(sc[t] - mx);
+        sc[t] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[4 + warp] = sum;
+    __syncthreads();
+    const float inv = 1.0f / (red[4] + red[5] + red[6] + red[7]);
+    // ---- out = sum_t p[t] V[t]
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int t0 = 0; t0 < T; t0 += 64) {
+        uint4 u[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int t = t0 + r * 16 + slot;
+            u[r] = (t < T) ? __ldg(V + (long long)t * 8 + chunk) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int t = t0 + r * 16 + slot;
+            const float w = (t < T) ? round_f16(sc[t] * inv) : 0.f;
+            const __half2* h2 = reinterpret_cast<const __half2*>(&u[r]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h2[j]);
+                acc[2 * j] = fmaf(w, f.x, acc[2 * j]);
+                acc[2 * j + 1] = fmaf(w, f.y, acc[2 * j + 1]);
+            }
+        }
+    }
+    // reduce over the 4 key slots inside a warp (lane bits 3,4), then over the 4 warps
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) osum[warp][lane * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const float v = osum[0][tid] + osum[1][tid] + osum[2][tid] + osum[3][tid];
+        out[(long long)b * n + h * 64 + tid] = __float2half_rn(v);
+    }
+}
+
+int launch_attn_dec_cross(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T,
+                          cudaStream_t s) {
+    if (T > kCrossMaxT) return set_error("attn_dec_cross: T %d > %d", T, kCrossMaxT);
+    dim3 grid(H, B);
+    attn_dec_cross_kernel<<<grid, kCrossThreads, 0, s>>>(q, kv, out, done, H, T);
+    WJB_CHECK_LAUNCH("attn_dec_cross");
+    return 0;
+}
+
+}  // namespace wjb

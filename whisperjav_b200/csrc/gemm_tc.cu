@@ -1,0 +1,346 @@
+// tcgen05 + TMA persistent GEMM for sm_100a:  out[r, n] = epilogue( sum_k A[r, k] * W[n, k] )
+//
+// Replaces the cuBLAS/cuDNN calls the reference reaches through torch (openai-whisper
+// model.py::Linear / Conv1d, called from whisperjav/modules/whisper_pro_asr.py:433).
+//
+//  * A is addressed through a 3-D TMA tensor map (k, row, batch) so that the k=3 convolutions
+//    run as im2col-free GEMMs: with channels-last activations [batch][T+2][C] the im2col row of
+//    output frame t is the contiguous span of 3*C halfs starting at padded row stride*t, i.e. a
+//    tensor whose row stride (stride*C) is smaller than its row length (3*C).
+//  * W is [N][K] row-major (torch Linear layout), 2-D tensor map.  Both operands are K-major,
+//    SWIZZLE_128B, 64-half (128 B) k-blocks.
+//  * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
+//    allocator, warps 4..11 = epilogue (TMEM -> registers -> fused bias/GELU/residual -> HBM).
+//    Two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
+//  * Epilogue keeps the rounding points of the reference's fp16 run: half(acc + bias), then
+//    GELU / residual / positional add each on the fp16-rounded value (see oracle/whisper_oracle.py).
+#include "kernels.h"
+
+namespace wjb {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;   // 64 halfs = 128 B = one SWIZZLE_128B row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kNumEpiWarps = 8;
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
+    static constexpr int kStageBytesB = BN * kBlockK * 2;
+    static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmDev {
+    const __half* bias;      // [N] or null
+    const __half* residual;  // indexed like out, or null
+    const float* pos;        // [rows_per_batch][N] fp32, added after GELU (encoder conv2), or null
+    __half* out;
+    long long out_row_stride;    // elements
+    long long out_batch_stride;  // elements
+    int rows_per_batch, n_batch, N, K;
+    int flags;
+    int hs_T, hs_H;  // head-split output: row (b, t) col c -> ((b*H + c/64)*T + t)*64 + c%64
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + Cfg::kStages;
+    uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
+    uint64_t* tempty_bar = bars + 2 * Cfg::kStages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m_tiles_per_batch = (p.rows_per_batch + kBlockM - 1) / kBlockM;
+    const int tiles_m = m_tiles_per_batch * p.n_batch;
+    const int tiles_n = (p.N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], kNumEpiWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % tiles_n, mt = tile / tiles_n;
+                const int b = mt / m_tiles_per_batch;
+                const int row0 = (mt % m_tiles_per_batch) * kBlockM;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                    uint8_t* sb = sa + Cfg::kStageBytesA;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_3d(sa, &tmA, &full_bar[stage], kb * kBlockK, row0, b);
+                    tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, nt * BN);
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(kBlockM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t sb = sa + Cfg::kStageBytesA;
+                    const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
+                    const uint64_t db = make_smem_desc(sb, 16, 1024, kLayoutSW128);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        // advance 32 B (16 halfs) inside the 128 B swizzle row: +2 in the >>4 address field
+                        umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                   // TMEM lane quadrant this warp may read
+        const int ch = (warp - kEpiWarp0) >> 2;   // column half
+        constexpr int kColsPerWarp = BN / 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int nt = tile % tiles_n, mt = tile / tiles_n;
+            const int b = mt / m_tiles_per_batch;
+            const int row = (mt % m_tiles_per_batch) * kBlockM + q * 32 + lane;
+            const bool row_ok = row < p.rows_per_batch;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + ch * kColsPerWarp;
+#pragma unroll 1
+            for (int c = 0; c < kColsPerWarp; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr0 + c, r);
+                tmem_ld_wait();
+                const int col0 = nt * BN + ch * kColsPerWarp + c;
+                if (row_ok && col0 < p.N) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.bias) {
+                        const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            uint4 bb = __ldg(bp + j4);
+                            const __half2* h2 = reinterpret_cast<const __half2*>(&bb);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float2 f = __half22float2(h2[j]);
+                                v[j4 * 8 + 2 * j] += f.x;
+                                v[j4 * 8 + 2 * j + 1] += f.y;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = round_f16(v[j]);
+                    if (p.flags & GEMM_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = round_f16(gelu_erf(v[j]));
+                    }
+                    long long off;
+                    if (p.flags & GEMM_HEADSPLIT) {
+                        off = ((long long)(b * p.hs_H + col0 / 64) * p.hs_T + row) * 64 + (col0 % 64);
+                    } else {
+                        off = (long long)b * p.out_batch_stride + (long long)row * p.out_row_stride + col0;
+                    }
+                    if (p.pos) {
+                        const float4* pp = reinterpret_cast<const float4*>(p.pos + (long long)row * p.N + col0);
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            float4 f = __ldg(pp + j4);
+                            v[j4 * 4 + 0] += f.x;
+                            v[j4 * 4 + 1] += f.y;
+                            v[j4 * 4 + 2] += f.z;
+                            v[j4 * 4 + 3] += f.w;
+                        }
+                    }
+                    if (p.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            uint4 rr = __ldg(rp + j4);
+                            const __half2* h2 = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float2 f = __half22float2(h2[j]);
+                                v[j4 * 8 + 2 * j] += f.x;
+                                v[j4 * 8 + 2 * j + 1] += f.y;
+                            }
+                        }
+                    }
+                    if (col0 + 32 <= p.N) {
+                        uint4* op = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            uint4 o;
+                            __half2* h2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(v[j4 * 8 + 2 * j], v[j4 * 8 + 2 * j + 1]);
+                            op[j4] = o;
+                        }
+                    } else {
+                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) p.out[off + j] = __float2half_rn(v[j]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+    auto fn = get_tensor_map_encoder();
+    if (!fn) return set_error("cuTensorMapEncodeTiled unavailable");
+    uint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu", (int)r, rank,
+                                            (unsigned long long)dims[0], (unsigned long long)dims[1]);
+    return 0;
+}
+
+template <int BN>
+static int launch_bn(const GemmArgs& a, const CUtensorMap& tmA, const GemmDev& d, int num_tiles, cudaStream_t stream) {
+    CUtensorMap tmB;
+    uint64_t dimsB[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    uint64_t strB[1] = {(uint64_t)a.ldw * 2};
+    uint32_t boxB[2] = {(uint32_t)kBlockK, (uint32_t)BN};
+    if (int e = encode_map(&tmB, a.W, 2, dimsB, strB, boxB)) return e;
+    int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+    gemm_tc_kernel<BN><<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(tmA, tmB, d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("gemm_tc launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int gemm_init() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes)) != cudaSuccess)
+        return set_error("gemm_init: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+    {
+        static bool inited = false;
+        if (!inited) {
+            if (int e = gemm_init()) return e;
+            inited = true;
+        }
+    }
+    if ((a.bias || a.residual || a.pos) && (a.N % 32)) return set_error("gemm: bias/residual/pos need N %% 32 == 0");
+    if (a.K % 8 != 0 || a.ldw % 8 != 0) return set_error("gemm: K and ldw must be multiples of 8 (16-byte TMA rows)");
+    if ((a.a_row_stride % 8) || (a.a_batch_stride % 8)) return set_error("gemm: A strides must be multiples of 8 halfs");
+    CUtensorMap tmA;
+    uint64_t dimsA[3] = {(uint64_t)a.K, (uint64_t)a.rows_per_batch, (uint64_t)a.n_batch};
+    uint64_t strA[2] = {(uint64_t)a.a_row_stride * 2, (uint64_t)(a.n_batch > 1 ? a.a_batch_stride : a.a_row_stride * (long long)a.rows_per_batch) * 2};
+    if (strA[1] == 0) strA[1] = 16;
+    uint32_t boxA[3] = {(uint32_t)kBlockK, (uint32_t)kBlockM, 1};
+    if (int e = encode_map(&tmA, a.A, 3, dimsA, strA, boxA)) return e;
+    GemmDev d;
+    d.bias = a.bias;
+    d.residual = a.residual;
+    d.pos = a.pos;
+    d.out = a.out;
+    d.out_row_stride = a.out_row_stride;
+    d.out_batch_stride = a.out_batch_stride;
+    d.rows_per_batch = a.rows_per_batch;
+    d.n_batch = a.n_batch;
+    d.N = a.N;
+    d.K = a.K;
+    d.flags = a.flags;
+    d.hs_T = a.hs_T;
+    d.hs_H = a.hs_H;
+    const int tiles_m = ((a.rows_per_batch + kBlockM - 1) / kBlockM) * a.n_batch;
+    int bn = a.block_n;
+    if (bn == 0) {
+        // enough tiles to fill the machine with the widest tile that still gives >= 1 wave
+        bn = 256;
+        if (tiles_m * ((a.N + 255) / 256) < sm_count()) bn = 128;
+        if (tiles_m * ((a.N + 127) / 128) < sm_count()) bn = 64;
+    }
+    const int tiles = tiles_m * ((a.N + bn - 1) / bn);
+    switch (bn) {
+        case 256: return launch_bn<256>(a, tmA, d, tiles, stream);
+        case 128: return launch_bn<128>(a, tmA, d, tiles, stream);
+        case 64: return launch_bn<64>(a, tmA, d, tiles, stream);
+    }
+    return set_error("gemm: unsupported block_n %d", bn);
+}
+
+}  // namespace wjb

@@ -1,0 +1,98 @@
+// Internal launch interfaces shared by the .cu files of libwjb200.so (not part of the C-ABI).
+#pragma once
+#include "common.cuh"
+
+namespace wjb {
+
+// ---- error plumbing (api.cu) -------------------------------------------------------------
+int set_error(const char* fmt, ...);  // records the message, returns a non-zero status
+int sm_count();
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+tensor_map_encode_fn get_tensor_map_encoder();
+
+#define WJB_CHECK_LAUNCH(name)                                                              \
+    do {                                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                               \
+        if (e__ != cudaSuccess) return ::wjb::set_error("%s: %s", name, cudaGetErrorString(e__)); \
+    } while (0)
+
+// ---- GEMM (gemm_tc.cu) ---------------------------------------------------------------------
+enum { GEMM_GELU = 1, GEMM_HEADSPLIT = 2 };
+struct GemmArgs {
+    const __half* A = nullptr;      // activations, addressed as [n_batch][rows_per_batch][K] with the strides below
+    long long a_row_stride = 0;     // halfs (may be < K: overlapping im2col rows)
+    long long a_batch_stride = 0;   // halfs
+    int rows_per_batch = 0, n_batch = 1, K = 0;
+    const __half* W = nullptr;      // [N][ldw]
+    int N = 0, ldw = 0;
+    const __half* bias = nullptr;
+    const __half* residual = nullptr;
+    const float* pos = nullptr;
+    __half* out = nullptr;
+    long long out_row_stride = 0, out_batch_stride = 0;
+    int flags = 0;
+    int hs_T = 0, hs_H = 0;
+    int block_n = 0;                // 0 = auto
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+int gemm_init();  // set kernel attributes up front (outside any stream capture)
+
+// ---- elementwise / normalisation (elementwise.cu) ------------------------------------------
+int launch_layernorm(const __half* x, const __half* gamma, const __half* beta, __half* out, int rows, int n, cudaStream_t s);
+int launch_im2col_k3(const __half* xpad, __half* out, int B, int T_out, int C, int stride, int T_in_padded, cudaStream_t s);
+
+// ---- log-mel (logmel.cu) -------------------------------------------------------------------
+struct LogmelArgs {
+    const float* audio;          // [n_clips][audio_stride] fp32
+    long long audio_stride;
+    const int* n_samples;        // device [n_clips]: valid samples per clip (rest is zero)
+    int n_clips;
+    int n_mels;
+    const float* filters;        // device [n_mels][201] fp32 (Slaney mel filterbank)
+    __half* out;                 // see layout
+    int time_major;              // 1: out[clip][row0 + t][n_mels] (row stride n_mels); 0: out[clip][n_mels][n_frames]
+    long long out_clip_stride;   // halfs
+    int row0;                    // first written row in the time-major layout (1 = leave a zero pad row for conv1)
+    int n_frames;                // frames written per clip; frames >= n_samples/160 are literal zeros (pad_or_trim)
+    int reflect_total;           // 0: signal is followed by >= 200 zeros (transcribe's padding=N_SAMPLES); else reflect at this length
+    float* clip_max;             // device [n_clips] workspace (log10 max per clip)
+    int* mel_range;              // device [2*n_mels] workspace (non-zero span of each filter row)
+};
+int launch_logmel(const LogmelArgs& a, cudaStream_t s);
+
+// ---- attention (attention.cu) --------------------------------------------------------------
+// Encoder self-attention over qkv [B*T][3n] (q | k | v, heads of 64), out [B*T][n].
+int launch_attn_encoder(const __half* qkv, __half* out, int B, int T, int H, cudaStream_t s);
+int attn_init();
+// Decoder single-token self-attention with HBM KV cache [B][2H][n_ctx][64] (K heads then V heads).
+int launch_attn_dec_self(const __half* qkv, __half* kv_cache, __half* out, const int* step, const unsigned char* done, int B, int H,
+                         int n_ctx, cudaStream_t s);
+// Decoder single-token cross-attention over kv [B][2H][T][64].
+int launch_attn_dec_cross(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T,
+                          cudaStream_t s);
+
+// ---- decoder token logic (decode.cu) -------------------------------------------------------
+struct DecodeCtl {            // device-resident control block, one per decode run
+    int step;                 // absolute position of the token being fed (0-based)
+    int n_initial;            // number of forced initial tokens (sample_begin)
+    int sot_index;
+    int max_steps;            // sample_len
+    int n_done;
+};
+struct DecodeParams {
+    int B, n_vocab, logits_stride;
+    int eot, no_speech, no_timestamps, timestamp_begin;
+    int suppress_blank, blank_token, apply_timestamp_rules, max_initial_timestamp_index;  // -1 = none
+    int n_ctx;
+    int tokens_stride;        // ints per row in tokens[]
+};
+int launch_embed(const int* tokens, int tokens_stride, const __half* emb, const __half* pos, __half* x, const DecodeCtl* ctl, int B,
+                 int n, cudaStream_t s);
+int launch_sample(const __half* logits, const unsigned char* suppress_mask, int* tokens, const int* initial_tokens, float* sum_logprob,
+                  float* no_speech_prob, int* out_len, unsigned char* done, DecodeCtl* ctl, const DecodeParams& p, cudaStream_t s);
+
+// ---- VAD (vad.cu) --------------------------------------------------------------------------
+struct VadArgs;
+}  // namespace wjb

@@ -1,0 +1,455 @@
+"""B200-native Whisper model object: the drop-in for what ``whisper.load_model(name, device)``
+returns in the reference (whisperjav/modules/whisper_pro_asr.py:182) -- same ``transcribe(audio,
+**params)`` call and result dict (whisper_pro_asr.py:433; upstream whisper/transcribe.py).
+
+Python here owns tensors, host<->device copies and the seek/threshold bookkeeping; every
+arithmetic step (log-mel, encoder, cross-K/V, the whole greedy decode loop with its logit
+filters) runs in hand-written sm_100a kernels behind the C-ABI of libwjb200.so.  There is no
+CPU path: constructing the model without a CUDA device or without the library raises.
+
+Batching: the reference decodes one <=30 s window per ``model.decode`` call; here any number of
+independent clips advance through their seek loops in lock-step, ``max_batch`` windows per
+device pass (windows are independent because every reference preset sets
+``condition_on_previous_text=False``; prompts are still honoured per clip).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import zlib
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .synth import DIMS, Dims, synth_weights
+from .weights import pack_weights
+
+SAMPLE_RATE = 16000
+N_FFT = 400
+HOP_LENGTH = 160
+N_SAMPLES = 480000
+N_FRAMES = 3000
+LANGUAGES = ("en", "zh", "de", "es", "ru", "ko", "fr", "ja", "pt", "tr", "pl", "ca", "nl", "ar", "sv", "it", "id", "hi", "fi", "vi")
+
+# Non-speech symbol token ids of the multilingual vocabulary (upstream tokenizer.non_speech_tokens;
+# identical to the head of transformers' NON_SPEECH_TOKENS_MULTI).
+NON_SPEECH_TOKENS = (
+    1, 2, 7, 8, 9, 10, 14, 25, 26, 27, 28, 29, 31, 58, 59, 60, 61, 62, 63, 90, 91, 92, 93, 359, 503, 522, 542, 873, 893,
+    902, 918, 922, 931, 1350, 1853, 1982, 2460, 2627, 3246, 3253, 3268, 3536, 3846, 3961, 4183, 4667, 6585, 6647, 7273,
+    9061, 9383, 10428, 10929, 11938, 12033, 12331, 12562, 13793, 14157, 14635, 15265, 15618, 16553, 16604, 18362, 18956,
+    20075, 21675, 22520, 26130, 26161, 26435, 28279, 29464, 31650, 32302, 32470, 36865, 42863, 47425, 49870, 50254)
+
+
+def slaney_mel_filters(n_mels: int) -> np.ndarray:
+    """librosa.filters.mel(sr=16000, n_fft=400, n_mels) -- Slaney scale, Slaney norm; fp32 [n_mels, 201]."""
+    def hz2mel(f):
+        f = np.asarray(f, np.float64)
+        return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-30) / 1000.0) / (np.log(6.4) / 27.0), f * 3.0 / 200.0)
+
+    def mel2hz(m):
+        m = np.asarray(m, np.float64)
+        return np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), m * 200.0 / 3.0)
+
+    freqs = np.linspace(0.0, SAMPLE_RATE / 2, N_FFT // 2 + 1)
+    pts = mel2hz(np.linspace(hz2mel(0.0), hz2mel(SAMPLE_RATE / 2), n_mels + 2))
+    lower = (freqs[None, :] - pts[:-2, None]) / (pts[1:-1] - pts[:-2])[:, None]
+    upper = (pts[2:, None] - freqs[None, :]) / (pts[2:] - pts[1:-1])[:, None]
+    fb = np.maximum(0.0, np.minimum(lower, upper)) * (2.0 / (pts[2:] - pts[:-2]))[:, None]
+    return fb.astype(np.float32)
+
+
+class Tokens:
+    """Special-token ids (upstream tokenizer.py); ids, not strings, are what the device needs."""
+
+    def __init__(self, n_vocab: int, language: str = "ja", task: str = "transcribe"):
+        self.n_vocab = n_vocab
+        self.eot, self.sot = 50257, 50258
+        self.num_languages = n_vocab - 51765 - 1
+        base = self.sot + 1 + self.num_languages
+        self.translate, self.transcribe, self.sot_lm, self.sot_prev = base, base + 1, base + 2, base + 3
+        self.no_speech, self.no_timestamps, self.timestamp_begin = base + 4, base + 5, base + 6
+        if language not in LANGUAGES:
+            raise ValueError(f"unsupported language {language!r} (ids are tabulated for {LANGUAGES})")
+        if task not in ("transcribe", "translate"):
+            raise ValueError(f"unsupported task {task!r}")
+        self.language_token = self.sot + 1 + LANGUAGES.index(language)
+        self.task_token = self.transcribe if task == "transcribe" else self.translate
+        self.blank = 220
+
+    def sot_sequence(self, without_timestamps: bool) -> List[int]:
+        seq = [self.sot, self.language_token, self.task_token]
+        return seq + [self.no_timestamps] if without_timestamps else seq
+
+    def suppress_list(self, spec) -> List[int]:
+        if isinstance(spec, str):
+            spec = [int(t) for t in spec.split(",")]
+        spec = list(spec or [])
+        if -1 in spec:
+            spec = [t for t in spec if t >= 0] + list(NON_SPEECH_TOKENS)
+        spec += [self.transcribe, self.translate, self.sot, self.sot_prev, self.sot_lm, self.no_speech]
+        return sorted(set(spec))
+
+
+_detok_hook = None
+
+
+def set_detokenizer(fn) -> None:
+    """Install a real ``ids -> str`` detokenizer (e.g. a tiktoken/HF tokenizer when its vocabulary file
+    is available).  Without one a deterministic placeholder maps every id to one CJK code point."""
+    global _detok_hook
+    _detok_hook = fn
+
+
+def detokenize(ids: Sequence[int]) -> str:
+    if _detok_hook is not None:
+        return _detok_hook(list(ids))
+    return "".join(chr(0x4E00 + (int(t) % 20992)) for t in ids)
+
+
+def compression_ratio(text: str) -> float:
+    raw = text.encode("utf-8")
+    return len(raw) / len(zlib.compress(raw))
+
+
+@dataclass
+class DecodingResult:
+    tokens: List[int] = field(default_factory=list)
+    text: str = ""
+    avg_logprob: float = float("nan")
+    no_speech_prob: float = float("nan")
+    temperature: float = 0.0
+    compression_ratio: float = float("nan")
+    language: str = "ja"
+    sum_logprob: float = float("nan")
+
+
+_DECODE_KEYS = {"task", "language", "temperature", "sample_len", "best_of", "beam_size", "patience", "length_penalty",
+                "prompt", "prefix", "suppress_tokens", "suppress_blank", "without_timestamps", "max_initial_timestamp", "fp16"}
+
+
+class WhisperB200:
+    """Weights resident on one B200 + reusable workspaces; ``transcribe`` mirrors upstream's signature."""
+
+    def __init__(self, dims: Dims, state_dict: Dict[str, torch.Tensor], device: Union[str, int, torch.device] = "cuda",
+                 max_batch: int = 64):
+        if not torch.cuda.is_available():
+            raise _lib.WjbError("WhisperB200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.dims = dims
+        self.device = torch.device(device if device != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        self.max_batch = int(max_batch)
+        self.is_multilingual = dims.n_vocab >= 51865
+        with torch.cuda.device(self.device):
+            self._blob = pack_weights(dims, state_dict, self.device)
+            self._cdims = _lib.make_dims(dims)
+            h = C.c_void_p()
+            _lib.check(self.lib.wjb_model_create(C.byref(self._cdims), _lib.ptr(self._blob), C.byref(h)), "wjb_model_create")
+            self._h = h
+            self._filters = torch.from_numpy(slaney_mel_filters(dims.n_mels)).to(self.device)
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self.stats = {"windows": 0, "decode_steps": 0, "device_passes": 0}
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.wjb_model_destroy(self._h)
+            self._h = None
+        self._bufs.clear()
+        self._blob = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _buf(self, key: str, nbytes: int) -> torch.Tensor:
+        t = self._bufs.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    # ------------------------------------------------------------------ stages
+    def log_mel(self, audio: torch.Tensor, n_samples: torch.Tensor, n_frames: int = N_FRAMES, layout: str = "time",
+                reflect_total: int = 0) -> torch.Tensor:
+        """audio fp32 [B, S] on device, n_samples int32 [B] on device.
+        layout "time": fp16 [B, n_frames + 2, n_mels] (rows 0 / n_frames+1 are the conv zero pad);
+        layout "mel":  fp16 [B, n_mels, n_frames] (upstream layout)."""
+        B = audio.shape[0]
+        m = self.dims.n_mels
+        ws = self._buf("mel_ws", self.lib.wjb_logmel_workspace_bytes(B, m))
+        if layout == "time":
+            out = torch.zeros(B, n_frames + 2, m, dtype=torch.float16, device=self.device)
+            tm, stride, row0 = 1, (n_frames + 2) * m, 1
+        else:
+            out = torch.empty(B, m, n_frames, dtype=torch.float16, device=self.device)
+            tm, stride, row0 = 0, m * n_frames, 0
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.wjb_logmel_f16(_lib.ptr(audio), audio.stride(0), _lib.ptr(n_samples), B, m, _lib.ptr(self._filters),
+                                              _lib.ptr(out), tm, stride, row0, n_frames, reflect_total, _lib.ptr(ws),
+                                              _lib.stream_ptr()), "wjb_logmel_f16")
+        return out
+
+    def encode(self, mel_tm: torch.Tensor) -> torch.Tensor:
+        """mel_tm fp16 [B, 3002, n_mels] -> audio features fp16 [B, 1500, n_state]."""
+        B = mel_tm.shape[0]
+        d = self.dims
+        assert mel_tm.shape[1] == 2 * d.n_audio_ctx + 2 and mel_tm.shape[2] == d.n_mels and mel_tm.is_contiguous()
+        out = torch.empty(B, d.n_audio_ctx, d.n_audio_state, dtype=torch.float16, device=self.device)
+        nb = self.lib.wjb_encoder_workspace_bytes(self._h, B)
+        ws = self._buf("enc_ws", nb)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.wjb_encoder_forward(self._h, _lib.ptr(mel_tm), B, _lib.ptr(out), _lib.ptr(ws), nb, _lib.stream_ptr()),
+                       "wjb_encoder_forward")
+        return out
+
+    def decode_features(self, xa: torch.Tensor, *, language="ja", task="transcribe", without_timestamps=False,
+                        suppress_tokens="-1", suppress_blank=True, max_initial_timestamp: Optional[float] = 1.0,
+                        sample_len: Optional[int] = None, prompt: Optional[Sequence[int]] = None,
+                        prefix: Optional[Sequence[int]] = None, temperature: float = 0.0) -> List[DecodingResult]:
+        """Greedy decode of B windows (upstream DecodingTask.run, T == 0) in one device-resident loop."""
+        d = self.dims
+        B = xa.shape[0]
+        tok = Tokens(d.n_vocab, language, task)
+        n_ctx = d.n_text_ctx
+        sample_len = sample_len or n_ctx // 2
+        initial = tok.sot_sequence(without_timestamps)
+        if prefix:
+            pfx = list(prefix)
+            max_prefix_len = n_ctx // 2 - sample_len
+            initial = initial + (pfx[-max_prefix_len:] if max_prefix_len > 0 else [])
+        if prompt:
+            initial = [tok.sot_prev] + list(prompt)[-(n_ctx // 2 - 1):] + initial
+        n_initial = len(initial)
+        sample_len = min(sample_len, n_ctx - n_initial + 1)
+        stride = n_initial + sample_len + 1
+        opts = _lib.DecodeOpts()
+        opts.n_initial, opts.sot_index, opts.sample_len = n_initial, initial.index(tok.sot), sample_len
+        opts.eot, opts.no_speech, opts.no_timestamps, opts.timestamp_begin = tok.eot, tok.no_speech, tok.no_timestamps, tok.timestamp_begin
+        opts.suppress_blank, opts.blank_token = int(bool(suppress_blank)), tok.blank
+        opts.apply_timestamp_rules = int(not without_timestamps)
+        mi = -1
+        if not without_timestamps and max_initial_timestamp:
+            mi = round(max_initial_timestamp / (30.0 / d.n_audio_ctx))
+        opts.max_initial_timestamp_index = mi
+        opts.tokens_stride, opts.check_every = stride, 8
+
+        key = ("mask", str(suppress_tokens), language, task)
+        mask = self._bufs.get(key)
+        if suppress_tokens is None or suppress_tokens == "" or suppress_tokens == []:
+            mask = None
+        elif mask is None:
+            mk = torch.zeros(d.n_vocab, dtype=torch.uint8)
+            mk[tok.suppress_list(suppress_tokens)] = 1
+            mask = mk.to(self.device)
+            self._bufs[key] = mask
+        with torch.cuda.device(self.device):
+            kv_bytes = self.lib.wjb_cross_kv_bytes(self._h, B)
+            kv = self._buf("cross_kv", kv_bytes)
+            _lib.check(self.lib.wjb_cross_kv(self._h, _lib.ptr(xa), B, _lib.ptr(kv), _lib.stream_ptr()), "wjb_cross_kv")
+            ws_bytes = self.lib.wjb_decode_workspace_bytes(self._h, B)
+            ws = self._buf("dec_ws", ws_bytes)
+            out = self._buf("dec_out", B * (stride * 4 + 16)).view(torch.int32)
+            tokens = out[: B * stride].view(B, stride)
+            slp = out[B * stride: B * stride + B].view(torch.float32)
+            nsp = out[B * stride + B: B * stride + 2 * B].view(torch.float32)
+            olen = out[B * stride + 2 * B: B * stride + 3 * B]
+            tokens.zero_()
+            tokens[:, :n_initial] = torch.tensor(initial, dtype=torch.int32, device=self.device)
+            steps = C.c_int(0)
+            _lib.check(self.lib.wjb_decode_greedy(self._h, _lib.ptr(kv), B, C.byref(opts), _lib.ptr(mask), _lib.ptr(tokens),
+                                                 _lib.ptr(slp), _lib.ptr(nsp), _lib.ptr(olen), _lib.ptr(ws), ws_bytes,
+                                                 C.byref(steps), _lib.stream_ptr()), "wjb_decode_greedy")
+            host = out[: B * stride + 3 * B].cpu()  # the one device->host read of the decode
+        self.stats["decode_steps"] += steps.value
+        self.stats["windows"] += B
+        self.stats["device_passes"] += 1
+        h_tokens = host[: B * stride].view(B, stride).numpy()
+        h_slp = host[B * stride: B * stride + B].view(torch.float32).numpy()
+        h_nsp = host[B * stride + B: B * stride + 2 * B].view(torch.float32).numpy()
+        h_len = host[B * stride + 2 * B: B * stride + 3 * B].numpy()
+        results = []
+        for b in range(B):
+            ids = [int(t) for t in h_tokens[b, n_initial: n_initial + int(h_len[b])]]
+            text = detokenize([t for t in ids if t < tok.eot]).strip()
+            results.append(DecodingResult(tokens=ids, text=text, avg_logprob=float(h_slp[b]) / (len(ids) + 1),
+                                          no_speech_prob=float(h_nsp[b]), temperature=float(temperature),
+                                          compression_ratio=compression_ratio(text) if text else 0.0, language=language,
+                                          sum_logprob=float(h_slp[b])))
+        return results
+
+    # ------------------------------------------------------------------ upstream-shaped API
+    def transcribe(self, audio: Union[np.ndarray, torch.Tensor], **params) -> dict:
+        """``whisper_model.transcribe(audio, **params)`` (whisper_pro_asr.py:433)."""
+        return self.transcribe_batch([audio], **params)[0]
+
+    def transcribe_batch(self, audios: Sequence[Union[np.ndarray, torch.Tensor]], *, verbose=None,
+                         temperature: Union[float, Sequence[float]] = (0.0, 0.2, 0.4, 0.6, 0.8, 1.0),
+                         compression_ratio_threshold: Optional[float] = 2.4, logprob_threshold: Optional[float] = -1.0,
+                         no_speech_threshold: Optional[float] = 0.6, condition_on_previous_text: bool = True,
+                         initial_prompt: Optional[Sequence[int]] = None, word_timestamps: bool = False,
+                         carry_initial_prompt: bool = False, **decode_options) -> List[dict]:
+        """Independent clips (each: fp32 mono 16 kHz) -> one upstream-shaped result dict per clip."""
+        unknown = set(decode_options) - _DECODE_KEYS
+        if unknown:  # upstream: DecodingOptions(**kwargs) raises TypeError
+            raise TypeError(f"transcribe() got unexpected keyword arguments {sorted(unknown)}")
+        language = decode_options.pop("language", None) or "ja"
+        task = decode_options.pop("task", "transcribe")
+        decode_options.pop("fp16", None)
+        if decode_options.pop("beam_size", None) or (decode_options.pop("best_of", None) or 1) > 1:
+            import logging
+            logging.getLogger("whisperjav").warning("b200 backend: beam search / best_of not built yet; decoding greedily")
+        decode_options.pop("patience", None)
+        decode_options.pop("length_penalty", None)
+        temps = [temperature] if isinstance(temperature, (int, float)) else list(temperature)
+        d = self.dims
+        tok = Tokens(d.n_vocab, language, task)
+        n = len(audios)
+        arrs = [a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a) for a in audios]
+        arrs = [a.astype(np.float32, copy=False).reshape(-1) for a in arrs]
+        content = [len(a) // HOP_LENGTH for a in arrs]
+        state = [{"seek": 0, "all_tokens": list(initial_prompt or []), "reset": 0, "segments": []} for _ in range(n)]
+        init_len = len(initial_prompt or [])
+        for st in state:
+            st["reset"] = 0
+
+        # clip-level log-mel (content frames only), computed once per clip batch
+        mels = self._clip_mels(arrs, content)
+
+        while True:
+            active = [i for i in range(n) if state[i]["seek"] < content[i]]
+            if not active:
+                break
+            for c0 in range(0, len(active), self.max_batch):
+                chunk = active[c0: c0 + self.max_batch]
+                sizes = [min(N_FRAMES, content[i] - state[i]["seek"]) for i in chunk]
+                win = self._gather_windows(mels, chunk, [state[i]["seek"] for i in chunk], sizes)
+                xa = self.encode(win)
+                prompts = [state[i]["all_tokens"][state[i]["reset"]:] for i in chunk]
+                results = self._decode_with_prompts(xa, prompts, temps[0], language, task, decode_options)
+                for j, i in enumerate(chunk):
+                    self._advance(state[i], results[j], tok, sizes[j], no_speech_threshold, logprob_threshold,
+                                  condition_on_previous_text)
+        outs = []
+        for i in range(n):
+            toks = state[i]["all_tokens"][init_len:]
+            outs.append({"text": detokenize([t for t in toks if t < tok.eot]), "segments": state[i]["segments"], "language": language})
+        return outs
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _clip_mels(self, arrs: List[np.ndarray], content: List[int]):
+        """Upload clips (pinned -> device) and compute their content-frame log-mel, time-major."""
+        n = len(arrs)
+        if n == 0:
+            return None
+        max_s = max(max(len(a) for a in arrs), HOP_LENGTH)
+        max_f = max(max(content), 1)
+        host = torch.zeros(n, max_s, dtype=torch.float32).pin_memory()
+        for i, a in enumerate(arrs):
+            host[i, : len(a)] = torch.from_numpy(a)
+        ns = torch.tensor([len(a) for a in arrs], dtype=torch.int32)
+        dev_audio = host.to(self.device, non_blocking=True)
+        dev_ns = ns.to(self.device)
+        # frames per clip rounded so short clips still give one full window directly
+        nf = max(max_f, N_FRAMES)
+        return self.log_mel(dev_audio, dev_ns, n_frames=nf, layout="time"), nf
+
+    def _gather_windows(self, mels, chunk: List[int], seeks: List[int], sizes: List[int]) -> torch.Tensor:
+        mel, nf = mels
+        m = self.dims.n_mels
+        if nf == N_FRAMES and all(s == 0 for s in seeks):
+            idx = torch.tensor(chunk, device=self.device)
+            return mel.index_select(0, idx).contiguous()
+        win = torch.zeros(len(chunk), N_FRAMES + 2, m, dtype=torch.float16, device=self.device)
+        for j, (i, s, z) in enumerate(zip(chunk, seeks, sizes)):
+            win[j, 1: 1 + z] = mel[i, 1 + s: 1 + s + z]
+        return win
+
+    def _decode_with_prompts(self, xa, prompts, temperature, language, task, decode_options):
+        # windows with identical prompts share one device pass (the common case: no prompt at all)
+        groups: Dict[tuple, List[int]] = {}
+        for j, p in enumerate(prompts):
+            groups.setdefault(tuple(p), []).append(j)
+        results: List[Optional[DecodingResult]] = [None] * len(prompts)
+        for p, idxs in groups.items():
+            sub = xa if len(idxs) == len(prompts) else xa[torch.tensor(idxs, device=self.device)].contiguous()
+            res = self.decode_features(sub, language=language, task=task, prompt=list(p) or None, temperature=temperature,
+                                       **{k: v for k, v in decode_options.items() if k in
+                                          ("without_timestamps", "suppress_tokens", "suppress_blank", "max_initial_timestamp",
+                                           "sample_len", "prefix")})
+            for j, r in zip(idxs, res):
+                results[j] = r
+        return results
+
+    @staticmethod
+    def _advance(st: dict, result: DecodingResult, tok: Tokens, segment_size: int, no_speech_threshold, logprob_threshold,
+                 condition_on_previous_text: bool) -> None:
+        """One iteration of upstream transcribe()'s seek loop for one clip (thresholds, timestamp-token
+        slicing, seek advance)."""
+        seek = st["seek"]
+        tokens = result.tokens
+        if no_speech_threshold is not None:
+            should_skip = result.no_speech_prob > no_speech_threshold
+            if logprob_threshold is not None and result.avg_logprob > logprob_threshold:
+                should_skip = False
+            if should_skip:
+                st["seek"] = seek + segment_size
+                return
+        time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
+        precision = 0.02
+        fields = {"temperature": result.temperature, "avg_logprob": result.avg_logprob,
+                  "compression_ratio": result.compression_ratio, "no_speech_prob": result.no_speech_prob}
+
+        def seg(start, end, toks):
+            return {"seek": seek, "start": start, "end": end, "text": detokenize([t for t in toks if t < tok.eot]),
+                    "tokens": list(toks), **fields}
+
+        is_ts = [t >= tok.timestamp_begin for t in tokens]
+        single_ending = is_ts[-2:] == [False, True]
+        cuts = [k + 1 for k in range(len(tokens) - 1) if is_ts[k] and is_ts[k + 1]]
+        current = []
+        if cuts:
+            if single_ending:
+                cuts.append(len(tokens))
+            last = 0
+            for cut in cuts:
+                piece = tokens[last:cut]
+                current.append(seg(time_offset + (piece[0] - tok.timestamp_begin) * precision,
+                                   time_offset + (piece[-1] - tok.timestamp_begin) * precision, piece))
+                last = cut
+            if single_ending:
+                st["seek"] = seek + segment_size
+            else:
+                st["seek"] = seek + (tokens[last - 1] - tok.timestamp_begin) * 2
+        else:
+            duration = segment_size * HOP_LENGTH / SAMPLE_RATE
+            stamps = [t for t in tokens if t >= tok.timestamp_begin]
+            if stamps and stamps[-1] != tok.timestamp_begin:
+                duration = (stamps[-1] - tok.timestamp_begin) * precision
+            current.append(seg(time_offset, time_offset + duration, tokens))
+            st["seek"] = seek + segment_size
+        for s in current:
+            if s["start"] == s["end"] or s["text"].strip() == "":
+                s["text"], s["tokens"] = "", []
+        base = len(st["segments"])
+        st["segments"].extend({"id": base + k, **s} for k, s in enumerate(current))
+        st["all_tokens"].extend(t for s in current for t in s["tokens"])
+        if not condition_on_previous_text or result.temperature > 0.5:
+            st["reset"] = len(st["all_tokens"])
+
+
+def load_model(name: str = "large-v3", device: Union[str, torch.device] = "cuda", state_dict: Optional[dict] = None,
+               seed: int = 11, max_batch: int = 64) -> WhisperB200:
+    """``whisper.load_model(name, device)`` stand-in (whisper_pro_asr.py:182).  With no checkpoint
+    reachable (no network on either box) ``state_dict=None`` builds the seeded synthetic weights of
+    that architecture; pass a real openai- or HF-named ``state_dict`` to run real weights."""
+    if name not in DIMS:
+        raise RuntimeError(f"Model {name} not found; available models = {sorted(DIMS)}")
+    dims = DIMS[name]
+    if state_dict is None:
+        state_dict = synth_weights(dims, seed=seed)
+    return WhisperB200(dims, state_dict, device=device, max_batch=max_batch)

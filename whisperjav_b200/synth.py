@@ -93,7 +93,7 @@ def synth_weights(dims: Dims, seed: int = 11, dtype=torch.float16, eot_boost: fl
     w["encoder.conv1.bias"] = rn(n, std=0.1)
     w["encoder.conv2.weight"] = rn(n, n, 3, std=1.5 / math.sqrt(n * 3))
     w["encoder.conv2.bias"] = rn(n, std=0.1)
-    w["encoder.positional_embedding"] = _sinusoids(dims.n_audio_ctx, n).to(dtype)
+    w["encoder.positional_embedding"] = _sinusoids(dims.n_audio_ctx, n)  # fp32 buffer upstream
     for i in range(dims.n_audio_layer):
         p = f"encoder.blocks.{i}"
         ln(p + ".attn_ln", n)
