@@ -95,7 +95,8 @@ def test_greedy_tokens_match_oracle(tiny, clips, diag_dir, without_timestamps):
     for rep, g, r in zip(report, res, ref):
         if rep["first_divergence"] is None:
             identical += 1
-            assert abs(g.avg_logprob - r.avg_logprob) <= 2e-3
+            # logits are fp16 (upstream: fp16 matmul output, then .float()): one quantum is 2^-6 at |logit| ~ 16
+            assert abs(g.avg_logprob - r.avg_logprob) <= 2e-2
             assert abs(g.no_speech_prob - r.no_speech_prob) <= 1e-3 + 0.02 * r.no_speech_prob
         else:
             assert rep["oracle_margin_at_divergence"] is not None and rep["oracle_margin_at_divergence"] < NEAR_TIE, rep
@@ -103,17 +104,27 @@ def test_greedy_tokens_match_oracle(tiny, clips, diag_dir, without_timestamps):
 
 
 def test_transcribe_matches_oracle(tiny, clips, diag_dir):
+    """End to end (mel + encoder + decoder + seek loop all on the GPU vs all on the CPU).  The two encoders
+    agree to ~4e-3 relative, which moves logits by a few fp16 quanta, so token identity is required up to
+    the first step whose oracle top-2 margin is below NEAR_TIE_E2E."""
+    NEAR_TIE_E2E = 0.15
     dims, w, m = tiny
     kw = dict(language="ja", task="transcribe", temperature=0.0, no_speech_threshold=0.6, logprob_threshold=-1.0,
               compression_ratio_threshold=2.4, condition_on_previous_text=False, max_initial_timestamp=0.0)
     got = m.transcribe_batch(clips[:3], **kw)
+    report = []
     for a, g in zip(clips[:3], got):
         ref = wo.transcribe(w, dims, a, **kw)
-        assert len(ref["segments"]) == len(g["segments"]) or True
-        gt = [s["tokens"] for s in g["segments"]]
-        rt = [s["tokens"] for s in ref["segments"]]
-        (diag_dir / "transcribe_tiny.json").write_text(json.dumps({"gpu": gt, "ref": rt}))
-        # end-to-end (mel+encoder+decoder all on GPU vs all on CPU): first segment must agree
-        if rt and gt:
-            n = min(len(rt[0]), len(gt[0]), 8)
-            assert rt[0][:n] == gt[0][:n]
+        mel = wo.pad_or_trim(wo.log_mel_spectrogram(a, dims.n_mels, padding=wo.N_SAMPLES)[:, : len(a) // 160], wo.N_FRAMES)
+        first = wo.decode(w, dims, mel[None], wo.DecodingOptions(language="ja", max_initial_timestamp=0.0), True)[0]
+        gt = [t for s_ in g["segments"] for t in s_["tokens"]]
+        rt = [t for s_ in ref["segments"] for t in s_["tokens"]]
+        n = min(len(gt), len(rt), len(first.tokens))
+        div = next((i for i in range(n) if gt[i] != rt[i]), None)
+        report.append({"gpu": gt[:40], "ref": rt[:40], "div": div, "margin": first.margins[div] if div is not None else None})
+        assert g["language"] == "ja" and all(s_["end"] >= s_["start"] for s_ in g["segments"])
+        if div is not None:
+            assert first.margins[div] < NEAR_TIE_E2E, report[-1]
+        else:
+            assert [round(s_["start"], 2) for s_ in g["segments"]][:2] == [round(s_["start"], 2) for s_ in ref["segments"]][:2]
+    (diag_dir / "transcribe_tiny.json").write_text(json.dumps(report))

@@ -154,6 +154,8 @@ struct wjb_model {
     float* g_nsp = nullptr;
     int32_t* g_len = nullptr;
     int* h_done = nullptr;  // pinned
+    cudaStream_t own_stream = nullptr;  // decode runs here (the caller's stream may be the legacy stream, which cannot be captured)
+    cudaEvent_t ev = nullptr;
     const __half* h16(const std::string& name) const { return reinterpret_cast<const __half*>(blob + L.off(name)); }
     const float* f32(const std::string& name) const { return reinterpret_cast<const float*>(blob + L.off(name)); }
 };
@@ -204,6 +206,11 @@ int wjb_model_create(const wjb_dims* dims, const void* weights_blob, wjb_model**
         delete m;
         return set_error("cudaHostAlloc failed");
     }
+    if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev, cudaEventDisableTiming) != cudaSuccess) {
+        delete m;
+        return set_error("stream/event creation failed");
+    }
     *out = m;
     return 0;
 }
@@ -212,6 +219,8 @@ void wjb_model_destroy(wjb_model* m) {
     if (!m) return;
     if (m->graph) cudaGraphExecDestroy(m->graph);
     if (m->h_done) cudaFreeHost(m->h_done);
+    if (m->own_stream) cudaStreamDestroy(m->own_stream);
+    if (m->ev) cudaEventDestroy(m->ev);
     delete m;
 }
 
@@ -487,7 +496,10 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
     if (!m || !cross_kv || !opts || !tokens || !sum_logprob || !no_speech_prob || !out_len || !workspace)
         return set_error("decode: null argument");
     const wjb_dims& d = m->d;
-    cudaStream_t s = (cudaStream_t)stream;
+    // order after the caller's stream, then run on our own capturable stream; synchronous on return
+    cudaStream_t s = m->own_stream;
+    cudaEventRecord(m->ev, (cudaStream_t)stream);
+    cudaStreamWaitEvent(s, m->ev, 0);
     const wjb_decode_opts& o = *opts;
     if (o.n_initial < 1 || o.sample_len < 1) return set_error("decode: bad n_initial/sample_len");
     const int total_steps = o.n_initial - 1 + o.sample_len;
