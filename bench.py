@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-seconds/sec (RTFx), whisper-large-v3, 30 s windows at batch 64.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model large-v3] [--batch 64]
+
+One *step* = one pass of the ASR hot path over one batch of synthetic speech-shaped 30 s windows:
+fused log-mel -> Whisper encoder -> cross-K/V projection -> greedy decode with the logit filters
+(timestamps mode, until every row hits EOT or sample_len), synthetic seeded weights of the exact
+architecture (no checkpoints offline).  ``value`` times the step with the audio already resident in
+HBM; ``e2e`` times the public API (``WhisperB200.transcribe_batch``) from pinned host audio to result
+dicts on the host.  Under torchrun each rank runs its own batch (weak scaling, windows are independent)
+and the packed segment records are all-gathered over NCCL inside the timed region.
+
+``--impl reference`` times the CPU restatement of the reference's openai-whisper path (oracle/, the
+reference packages cannot be installed offline) on the host cores, one window per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "audio-seconds/sec (RTFx) whisper-large-v3 30s@b64"
+WINDOW_S = 30.0
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "tflops_burst": d.get("bf16_tflops", 1590.0),
+                "tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def enc_gemm_flops(d, B):
+    n, T, C = d.n_audio_state, d.n_audio_ctx, d.n_mels
+    conv = 2 * (2 * T) * n * 3 * C + 2 * T * n * 3 * n
+    per_layer = 2 * T * n * (3 * n) + 2 * T * n * n + 2 * 2 * T * n * 4 * n
+    return B * (conv + d.n_audio_layer * per_layer)
+
+
+def enc_attn_flops(d, B):
+    return B * d.n_audio_layer * 4 * d.n_audio_head * d.n_audio_ctx * d.n_audio_ctx * 64
+
+
+def decode_bytes(d, steps_run, active_steps_total, B):
+    """Algorithmic HBM bytes of a decode run: per step the decoder weights once, plus per
+    active row the cross-K/V of every layer; self-KV and logits are second order but counted."""
+    t = d.n_text_state
+    w_layer = (3 * t * t + t * t + t * t + t * t + 8 * t * t) * 2  # qkv, out, cq, cout, fc1+fc2 (cross k/v proj is per window)
+    weights = d.n_text_layer * w_layer + d.n_vocab * t * 2
+    cross = d.n_text_layer * 2 * d.n_audio_ctx * t * 2
+    logits = d.n_vocab * 2
+    return steps_run * weights + active_steps_total * (cross + logits)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from whisperjav_b200 import _lib, model as M
+    from whisperjav_b200.distributed import gather_segment_records, pack_records
+    from whisperjav_b200.synth import DIMS, speech_shaped_audio
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dims = DIMS[args.model]
+    B = args.batch
+    m = M.load_model(args.model, device=f"cuda:{local}", seed=11, max_batch=B)
+    lib = _lib.load()
+    # synthetic speech-shaped windows: 8 distinct clips tiled to B (generation is CPU-expensive)
+    base = [speech_shaped_audio(WINDOW_S, 1000 * 2 + rank * 64 + i) for i in range(min(8, B))]
+    clips = [base[i % len(base)] for i in range(B)]
+    host_audio = torch.stack([torch.from_numpy(c) for c in clips]).pin_memory()
+    dev_audio = host_audio.cuda()
+    ns = torch.full((B,), host_audio.shape[1], dtype=torch.int32, device="cuda")
+    dec_kw = dict(language="ja", task="transcribe", without_timestamps=False, max_initial_timestamp=0.0)
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def step_resident():
+        mel = m.log_mel(dev_audio, ns, n_frames=3000, layout="time")
+        xa = m.encode(mel)
+        res = m.decode_features(xa, **dec_kw)
+        if world > 1:
+            rec = pack_records([(rank * B + i, 0.0, WINDOW_S, r.avg_logprob, r.no_speech_prob, r.tokens) for i, r in enumerate(res)])
+            gather_segment_records(rec, device=f"cuda:{local}")
+        return res
+
+    def step_e2e():
+        out = m.transcribe_batch(clips, temperature=0.0, condition_on_previous_text=False, no_speech_threshold=0.6,
+                                 logprob_threshold=-1.0, compression_ratio_threshold=2.4, pinned_audio=host_audio, **dec_kw)
+        if world > 1:
+            rec = pack_records([(rank * B + i, 0.0, WINDOW_S, s["avg_logprob"], s["no_speech_prob"], s["tokens"])
+                                for i, o in enumerate(out) for s in o["segments"][:1]])
+            gather_segment_records(rec, device=f"cuda:{local}")
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        times, extra = [], []
+        for _ in range(steps):
+            l2_flush.fill_(1)  # flush L2 between timed iterations (inputs are also larger than L2)
+            barrier()
+            if profile:
+                lib.wjb_profile_enable(1)
+            s0 = dict(m.stats)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = fn()
+            e1.record()
+            barrier()
+            times.append(e0.elapsed_time(e1))
+            if profile:
+                import ctypes as C
+                ms = (C.c_float * 3)()
+                cnt = (C.c_int * 3)()
+                lib.wjb_profile_read(ms, cnt, 3)
+                lib.wjb_profile_enable(0)
+                extra.append({"ms": list(ms), "launches": list(cnt), "steps_run": m.stats["decode_steps"] - s0["decode_steps"], "res": res})
+        return times, extra
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # stage timing (events between stages) is taken on the same timed steps
+    stage = {"mel": [], "encoder": [], "decode": []}
+
+    def step_resident_staged():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        mel = m.log_mel(dev_audio, ns, n_frames=3000, layout="time")
+        ev[1].record()
+        xa = m.encode(mel)
+        ev[2].record()
+        res = m.decode_features(xa, **dec_kw)
+        ev[3].record()
+        if world > 1:
+            rec = pack_records([(rank * B + i, 0.0, WINDOW_S, r.avg_logprob, r.no_speech_prob, r.tokens) for i, r in enumerate(res)])
+            gather_segment_records(rec, device=f"cuda:{local}")
+        torch.cuda.synchronize()
+        stage["mel"].append(ev[0].elapsed_time(ev[1]))
+        stage["encoder"].append(ev[1].elapsed_time(ev[2]))
+        stage["decode"].append(ev[2].elapsed_time(ev[3]))
+        return res
+
+    times, extra = timed(step_resident_staged, args.steps, profile=True)
+    for _ in range(min(args.warmup, 1)):
+        step_e2e()
+    e2e_times, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    total_ms = max_over_ranks(sum(times))
+    e2e_ms = max_over_ranks(sum(e2e_times))
+    audio_s = world * B * WINDOW_S * args.steps
+    value = audio_s / (total_ms / 1e3)
+    e2e_value = audio_s / (e2e_ms / 1e3)
+
+    # ---- rooflines (rank 0's own step numbers) ------------------------------------------------
+    peaks = _peaks()
+    gemm_ms = np.mean([x["ms"][0] for x in extra])
+    attn_ms = np.mean([x["ms"][1] for x in extra])
+    gemm_launches = int(np.mean([x["launches"][0] for x in extra]))
+    attn_launches = int(np.mean([x["launches"][1] for x in extra]))
+    ln_launches = int(np.mean([x["launches"][2] for x in extra]))
+    gemm_tf = enc_gemm_flops(dims, B) / (gemm_ms / 1e3) / 1e12
+    attn_tf = enc_attn_flops(dims, B) / (attn_ms / 1e3) / 1e12
+    steps_run = float(np.mean([x["steps_run"] for x in extra]))
+    n_initial = 3
+    active = float(np.mean([sum(min(len(r.tokens) + 1 + (n_initial - 1), x["steps_run"]) for r in x["res"]) for x in extra]))
+    dec_ms = float(np.mean(stage["decode"]))
+    dec_gbs = decode_bytes(dims, steps_run, active, B) / (dec_ms / 1e3) / 1e9
+    mel_gbs = B * 2.688e6 / (np.mean(stage["mel"]) / 1e3) / 1e9
+    shares = {"encoder_gemm": gemm_ms, "encoder_attention": attn_ms, "decode": dec_ms, "mel": float(np.mean(stage["mel"]))}
+    dominant = max(shares, key=shares.get)
+    rl_all = {
+        "encoder_gemm": {"kernel": "gemm_tc_kernel (tcgen05)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["tflops_sustained"] / 1.0,
+                         "unit": "TFLOP/s", "frac": gemm_tf / peaks["tflops_sustained"], "traffic": None, "ms_per_step": gemm_ms,
+                         "launches_per_step": gemm_launches},
+        "encoder_attention": {"kernel": "attn_encoder_kernel (tcgen05)", "bound": "tensor", "achieved": attn_tf, "peak": peaks["tflops_sustained"],
+                              "unit": "TFLOP/s", "frac": attn_tf / peaks["tflops_sustained"], "traffic": None, "ms_per_step": attn_ms,
+                              "launches_per_step": attn_launches},
+        "decode": {"kernel": "decode step graph (attn_dec_cross_kernel dominant)", "bound": "hbm", "achieved": dec_gbs, "peak": peaks["hbm_gbs"],
+                   "unit": "GB/s", "frac": dec_gbs / peaks["hbm_gbs"], "traffic": None, "ms_per_step": dec_ms, "decoder_steps": steps_run},
+        "mel": {"kernel": "logmel_kernel", "bound": "hbm", "achieved": mel_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": mel_gbs / peaks["hbm_gbs"], "traffic": None, "ms_per_step": shares["mel"]},
+    }
+    roofline = dict(rl_all[dominant])
+    roofline["peak_source"] = peaks["source"] + (", sustained figure (kernel timed inside a long step)" if roofline["bound"] == "tensor" else "")
+    tokens_out = int(np.mean([sum(len(r.tokens) for r in x["res"]) for x in extra]))
+    n_layers_launch = dims.n_text_layer * 12 + 5
+    gpu_launches = int(3 + gemm_launches + attn_launches + ln_launches + dims.n_text_layer + steps_run * n_layers_launch)
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic (seeded speech-shaped 16 kHz audio; seeded random-init weights of the exact architecture)",
+            "config": {"workload": f"whisper-{args.model} full hot path: log-mel + encoder + cross-KV + greedy decode (timestamps mode, to EOT/sample_len), "
+                                   f"batch {B} x 30 s windows per GPU", "global_batch": world * B, "parallelism": f"dp{world} (windows sharded, weights replicated)",
+                       "l2": "L2 flushed (256 MiB write) between timed iterations; activations/weights also exceed L2",
+                       "decode_tokens_per_step": tokens_out, "decoder_steps": steps_run},
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(B * host_audio.shape[1] * 4),
+                    "d2h_bytes_per_step": int(B * (3 + 224 + 1 + 3) * 4), "ms_per_step": e2e_ms / args.steps,
+                    "api": "WhisperB200.transcribe_batch(host fp32 clips) -> result dicts"},
+            "gpu_launches": gpu_launches,
+            "clocks": clocks,
+            "roofline": roofline, "roofline_all": rl_all,
+            "stages_ms": {k: float(np.mean(v)) for k, v in stage.items()},
+            "encoder_tensor_util_pct_of_measured_peak": 100.0 * (enc_gemm_flops(dims, B) + enc_attn_flops(dims, B)) / ((gemm_ms + attn_ms) / 1e3) / 1e12 / peaks["tflops_sustained"],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.model, budget_s=25.0)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _cpu_window(model_name, sample_len, pw=None, dims=None, seed_audio=2000):
+    from oracle import whisper_oracle as wo
+    from whisperjav_b200.synth import speech_shaped_audio
+    a = speech_shaped_audio(WINDOW_S, seed_audio)
+    t0 = time.time()
+    mel = wo.pad_or_trim(wo.log_mel_spectrogram(a, dims.n_mels, padding=wo.N_SAMPLES)[:, : len(a) // 160], wo.N_FRAMES)
+    xa = wo.encoder_forward(pw, dims, mel[None], True)
+    t1 = time.time()
+    res = wo.decode(pw, dims, None, wo.DecodingOptions(language="ja", max_initial_timestamp=0.0, sample_len=sample_len), True, audio_features=xa)
+    t2 = time.time()
+    return t1 - t0, t2 - t1, len(res[0].tokens)
+
+
+def _cpu_setup(model_name):
+    from oracle import whisper_oracle as wo
+    from whisperjav_b200.synth import DIMS, synth_weights
+    torch.set_num_threads(os.cpu_count() or 1)
+    dims = DIMS[model_name]
+    pw = wo.prepare_weights(synth_weights(dims, seed=11), True)
+    return dims, pw
+
+
+def cpu_baseline(model_name, budget_s=25.0):
+    """The oracle (CPU restatement of the reference's openai-whisper path) timed on the host cores on a
+    bounded sample: one 30 s window, decode capped so the whole thing stays near ``budget_s``."""
+    dims, pw = _cpu_setup(model_name)
+    enc_s, dec_s, ntok = _cpu_window(model_name, 8, pw, dims)
+    per_tok = dec_s / max(ntok, 1)
+    cap = int(max(8, min(224, (budget_s - enc_s) / max(per_tok, 1e-3))))
+    enc_s, dec_s, ntok = _cpu_window(model_name, cap, pw, dims)
+    wall = enc_s + dec_s
+    return {"value": WINDOW_S / wall, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"1 window of 30 s, whisper-{model_name}: mel+encoder {enc_s:.1f} s, greedy decode capped at {cap} tokens "
+                      f"({ntok} produced, {dec_s:.1f} s); batch 1 per call as the reference runs it; torch CPU fp32 with fp16 rounding points",
+            "note": "restated CPU path of openai-whisper @ c0d2f62 on synthetic weights (reference packages not installable offline); baseline only"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    dims, pw = _cpu_setup(args.model)
+    enc_s, dec_s, ntok = _cpu_window(args.model, 4, pw, dims)
+    per_tok = dec_s / max(ntok, 1)
+    per_step_budget = 170.0 / max(1, args.steps + args.warmup)
+    cap = int(max(4, min(224, (per_step_budget - enc_s) / max(per_tok, 1e-3))))
+    for i in range(args.warmup):
+        _cpu_window(args.model, cap, pw, dims, 2000 + i)
+    t0 = time.time()
+    toks = 0
+    for i in range(args.steps):
+        _, _, n = _cpu_window(args.model, cap, pw, dims, 3000 + i)
+        toks += n
+    wall = time.time() - t0
+    value = args.steps * WINDOW_S / wall
+    cb = {"value": value, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+          "sample": f"{args.steps} steps x 1 window of 30 s (batch 1 per call, as the reference does), greedy decode capped at {cap} tokens per window"}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (fp16 rounding points)", "data": "synthetic (same generators as the GPU arm)",
+        "config": {"workload": f"whisper-{args.model} full hot path on host cores, 1 window per step", "note":
+                   "oracle port of openai-whisper @ c0d2f62; the reference's own packages cannot be installed offline"},
+        "cpu_baseline": cb, "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="large-v3")
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -116,6 +116,11 @@ int wjb_attention_encoder_f16(const void* qkv, void* out, int batch, int T, int 
 /* single decoder step pieces */
 int wjb_attention_cross_f16(const void* q, const void* kv, void* out, int batch, int n_head, int T, void* stream);
 
+/* ---- per-kernel-class timing of wjb_encoder_forward (CUDA events on the launching stream) ------
+ * classes: 0 = tcgen05 GEMM (conv1/conv2/linear), 1 = encoder attention, 2 = LayerNorm.  Off by default. */
+void wjb_profile_enable(int on);
+int wjb_profile_read(float* ms_by_class, int* launches_by_class, int n_classes);
+
 /* ---- voice-activity gate ----------------------------------------------------------------------
  * Replaces the per-window model calls inside `get_speech_timestamps(tensor, jit_model)` at
  * modules/speech_segmentation/backends/silero.py:269-273 (and silero_v6.py:205-210; the per-hop

@@ -153,10 +153,27 @@ class Rounder:
         return t.half().float() if self.on else t
 
 
+class PreparedWeights(dict):
+    """fp32 copies of the weights, already rounded the way the run will use them (see prepare_weights)."""
+
+
+def prepare_weights(weights: Dict[str, torch.Tensor], sim_fp16: bool = True) -> "PreparedWeights":
+    """Convert once instead of per call: fp32 tensors, fp16-rounded when ``sim_fp16`` (what
+    ``weight.to(x.dtype)`` yields upstream).  LayerNorm parameters and positional buffers stay fp32."""
+    out = PreparedWeights()
+    for k, v in weights.items():
+        f = v.float()
+        keep = ("_ln." in k or ".ln." in k or ".ln_post." in k or k.endswith("positional_embedding"))
+        out[k] = f if (keep or not sim_fp16) else f.half().float()
+    return out
+
+
 def _w(weights: Dict[str, torch.Tensor], name: str, r: Rounder) -> Optional[torch.Tensor]:
     t = weights.get(name)
     if t is None:
         return None
+    if isinstance(weights, PreparedWeights):
+        return t
     return r(t.float())
 
 

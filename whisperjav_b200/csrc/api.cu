@@ -47,6 +47,40 @@ tensor_map_encode_fn get_tensor_map_encoder() {
 
 int sample_init();
 
+// ---- optional per-kernel-class timing (CUDA events on the launching stream) -----------------
+enum { PC_GEMM = 0, PC_ATTN = 1, PC_LN = 2, PC_N = 3 };
+struct ProfRec {
+    int cls;
+    cudaEvent_t a, b;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_ev_pool;
+static cudaEvent_t prof_event() {
+    if (!g_ev_pool.empty()) {
+        cudaEvent_t e = g_ev_pool.back();
+        g_ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    int idx = -1;
+    cudaStream_t s;
+    ProfScope(int cls, cudaStream_t st) : s(st) {
+        if (!g_prof_on) return;
+        ProfRec r{cls, prof_event(), prof_event()};
+        cudaEventRecord(r.a, s);
+        g_prof.push_back(r);
+        idx = (int)g_prof.size() - 1;
+    }
+    ~ProfScope() {
+        if (idx >= 0) cudaEventRecord(g_prof[idx].b, s);
+    }
+};
+
 static int init_kernels() {
     static bool done = false;
     if (done) return 0;
@@ -308,7 +342,10 @@ int wjb_encoder_forward(wjb_model* m, const void* mel_tm, int batch, void* out, 
     g.out_row_stride = n;
     g.out_batch_stride = (long long)T2 * n;
     g.flags = GEMM_GELU;
-    if (int e = launch_gemm(g, s)) return e;
+    {
+        ProfScope ps(PC_GEMM, s);
+        if (int e = launch_gemm(g, s)) return e;
+    }
     // conv2 (stride 2) + GELU + positional embedding -> x [B][T][n]
     g = GemmArgs();
     g.A = w.c1;
@@ -326,7 +363,10 @@ int wjb_encoder_forward(wjb_model* m, const void* mel_tm, int batch, void* out, 
     g.out_row_stride = n;
     g.out_batch_stride = (long long)T * n;
     g.flags = GEMM_GELU;
-    if (int e = launch_gemm(g, s)) return e;
+    {
+        ProfScope ps(PC_GEMM, s);
+        if (int e = launch_gemm(g, s)) return e;
+    }
 
     const int M = B * T;
     auto linear = [&](const __half* A, int K, const __half* W, const __half* bias, const __half* res, __half* o, int N, int flags) {
@@ -346,17 +386,24 @@ int wjb_encoder_forward(wjb_model* m, const void* mel_tm, int batch, void* out, 
         q.flags = flags;
         return launch_gemm(q, s);
     };
+    auto ln = [&](const __half* x, const __half* g_, const __half* b_, __half* o) {
+        ProfScope ps(PC_LN, s);
+        return launch_layernorm(x, g_, b_, o, M, n, s);
+    };
     for (int i = 0; i < d.n_audio_layer; ++i) {
         const std::string p = "enc." + std::to_string(i) + ".";
-        if (int e = launch_layernorm(w.x, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"), w.h, M, n, s)) return e;
+        if (int e = ln(w.x, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"), w.h)) return e;
         if (int e = linear(w.h, n, m->h16(p + "qkv.w"), m->h16(p + "qkv.b"), nullptr, w.qkv, 3 * n, 0)) return e;
-        if (int e = launch_attn_encoder(w.qkv, w.h, B, T, H, s)) return e;
+        {
+            ProfScope ps(PC_ATTN, s);
+            if (int e = launch_attn_encoder(w.qkv, w.h, B, T, H, s)) return e;
+        }
         if (int e = linear(w.h, n, m->h16(p + "out.w"), m->h16(p + "out.b"), w.x, w.x, n, 0)) return e;
-        if (int e = launch_layernorm(w.x, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"), w.h, M, n, s)) return e;
+        if (int e = ln(w.x, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"), w.h)) return e;
         if (int e = linear(w.h, n, m->h16(p + "fc1.w"), m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, GEMM_GELU)) return e;
         if (int e = linear(w.mlp, 4 * n, m->h16(p + "fc2.w"), m->h16(p + "fc2.b"), w.x, w.x, n, 0)) return e;
     }
-    return launch_layernorm(w.x, m->h16("enc.ln_post.g"), m->h16("enc.ln_post.b"), reinterpret_cast<__half*>(out), M, n, s);
+    return ln(w.x, m->h16("enc.ln_post.g"), m->h16("enc.ln_post.b"), reinterpret_cast<__half*>(out));
 }
 
 // ------------------------------------------------------------------ cross K/V
@@ -577,6 +624,28 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
     }
     if ((ce = cudaStreamSynchronize(s)) != cudaSuccess) return set_error("decode: final sync: %s", cudaGetErrorString(ce));
     if (steps_run) *steps_run = step;
+    return 0;
+}
+
+// ------------------------------------------------------------------ profiling
+void wjb_profile_enable(int on) { g_prof_on = on != 0; }
+
+int wjb_profile_read(float* ms_by_class, int* launches_by_class, int n_classes) {
+    for (int i = 0; i < n_classes; ++i) {
+        if (ms_by_class) ms_by_class[i] = 0.f;
+        if (launches_by_class) launches_by_class[i] = 0;
+    }
+    for (auto& r : g_prof) {
+        cudaEventSynchronize(r.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.cls < n_classes) {
+            if (ms_by_class) ms_by_class[r.cls] += ms;
+            if (launches_by_class) launches_by_class[r.cls] += 1;
+        }
+        g_ev_pool.push_back(r.a);
+        g_ev_pool.push_back(r.b);
+    }
+    g_prof.clear();
     return 0;
 }
 

@@ -150,6 +150,7 @@ class WhisperB200:
             self._h = h
             self._filters = torch.from_numpy(slaney_mel_filters(dims.n_mels)).to(self.device)
         self._bufs: Dict[str, torch.Tensor] = {}
+        self._pinned: Dict[str, torch.Tensor] = {}
         self.stats = {"windows": 0, "decode_steps": 0, "device_passes": 0}
 
     # ------------------------------------------------------------------ plumbing
@@ -292,7 +293,8 @@ class WhisperB200:
                          compression_ratio_threshold: Optional[float] = 2.4, logprob_threshold: Optional[float] = -1.0,
                          no_speech_threshold: Optional[float] = 0.6, condition_on_previous_text: bool = True,
                          initial_prompt: Optional[Sequence[int]] = None, word_timestamps: bool = False,
-                         carry_initial_prompt: bool = False, **decode_options) -> List[dict]:
+                         carry_initial_prompt: bool = False, pinned_audio: Optional[torch.Tensor] = None,
+                         **decode_options) -> List[dict]:
         """Independent clips (each: fp32 mono 16 kHz) -> one upstream-shaped result dict per clip."""
         unknown = set(decode_options) - _DECODE_KEYS
         if unknown:  # upstream: DecodingOptions(**kwargs) raises TypeError
@@ -318,7 +320,7 @@ class WhisperB200:
             st["reset"] = 0
 
         # clip-level log-mel (content frames only), computed once per clip batch
-        mels = self._clip_mels(arrs, content)
+        mels = self._clip_mels(arrs, content, pinned_audio)
 
         while True:
             active = [i for i in range(n) if state[i]["seek"] < content[i]]
@@ -341,16 +343,25 @@ class WhisperB200:
         return outs
 
     # -- helpers -------------------------------------------------------------------------------
-    def _clip_mels(self, arrs: List[np.ndarray], content: List[int]):
-        """Upload clips (pinned -> device) and compute their content-frame log-mel, time-major."""
+    def _clip_mels(self, arrs: List[np.ndarray], content: List[int], pinned: Optional[torch.Tensor] = None):
+        """Upload clips (pinned -> device) and compute their content-frame log-mel, time-major.
+        ``pinned``: optional caller-owned pinned fp32 [n, S] tensor already holding the clips (skips staging)."""
         n = len(arrs)
         if n == 0:
             return None
         max_s = max(max(len(a) for a in arrs), HOP_LENGTH)
         max_f = max(max(content), 1)
-        host = torch.zeros(n, max_s, dtype=torch.float32).pin_memory()
-        for i, a in enumerate(arrs):
-            host[i, : len(a)] = torch.from_numpy(a)
+        if pinned is not None and pinned.shape[0] == n and pinned.shape[1] >= max_s and pinned.is_pinned():
+            host = pinned
+        else:
+            host = self._pinned.get("audio")
+            if host is None or host.shape[0] < n or host.shape[1] < max_s:
+                host = torch.zeros(n, max_s, dtype=torch.float32).pin_memory()
+                self._pinned["audio"] = host
+            host = host[:n, :max_s]
+            for i, a in enumerate(arrs):
+                host[i, : len(a)] = torch.from_numpy(a)
+                host[i, len(a):] = 0
         ns = torch.tensor([len(a) for a in arrs], dtype=torch.int32)
         dev_audio = host.to(self.device, non_blocking=True)
         dev_ns = ns.to(self.device)

@@ -53,8 +53,9 @@ def _sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> to
     return torch.cat([torch.sin(t), torch.cos(t)], dim=1)
 
 
-def synth_weights(dims: Dims, seed: int = 11, dtype=torch.float16, eot_boost: float = 1.5,
-                  logit_std: float = 3.0, attn_logit_std: float = 10.0, res_gain: float = None) -> Dict[str, torch.Tensor]:
+def synth_weights(dims: Dims, seed: int = 11, dtype=torch.float16, eot_boost: float = 1.8,
+                  logit_std: float = 3.0, attn_logit_std: float = 10.0, res_gain: float = None,
+                  cross_gain: float = 0.3, bias_std: float = 0.02) -> Dict[str, torch.Tensor]:
     """Seeded weights in openai-whisper ``state_dict`` naming.  Stored in ``dtype`` (fp16:
     what the reference's ``fp16=True`` run holds after ``model.half()``)."""
     g = torch.Generator().manual_seed(seed)
@@ -68,25 +69,25 @@ def synth_weights(dims: Dims, seed: int = 11, dtype=torch.float16, eot_boost: fl
 
     def ln(prefix, n):
         w[prefix + ".weight"] = (1.0 + 0.1 * torch.randn(n, generator=g)).to(dtype)
-        w[prefix + ".bias"] = rn(n, std=0.1)
+        w[prefix + ".bias"] = rn(n, std=bias_std)
 
-    def attn(prefix, n, n_head):
+    def attn(prefix, n, n_head, gain=1.0):
         d = n // n_head
         # q.k/sqrt(d) with unit-variance inputs has std  sq*sk*n*sqrt(d)/sqrt(d) = sq*sk*n
         s_qk = math.sqrt(attn_logit_std / n)
         w[prefix + ".query.weight"] = rn(n, n, std=s_qk)
-        w[prefix + ".query.bias"] = rn(n, std=0.1)
+        w[prefix + ".query.bias"] = rn(n, std=bias_std)
         w[prefix + ".key.weight"] = rn(n, n, std=s_qk)
         w[prefix + ".value.weight"] = rn(n, n, std=1.0 / math.sqrt(n))
-        w[prefix + ".value.bias"] = rn(n, std=0.1)
-        w[prefix + ".out.weight"] = rn(n, n, std=res_gain / math.sqrt(n))
-        w[prefix + ".out.bias"] = rn(n, std=0.05)
+        w[prefix + ".value.bias"] = rn(n, std=bias_std)
+        w[prefix + ".out.weight"] = rn(n, n, std=gain * res_gain / math.sqrt(n))
+        w[prefix + ".out.bias"] = rn(n, std=0.5 * bias_std)
 
     def mlp(prefix, n):
         w[prefix + ".0.weight"] = rn(4 * n, n, std=1.0 / math.sqrt(n))
-        w[prefix + ".0.bias"] = rn(4 * n, std=0.1)
+        w[prefix + ".0.bias"] = rn(4 * n, std=bias_std)
         w[prefix + ".2.weight"] = rn(n, 4 * n, std=0.8 * res_gain / math.sqrt(4 * n))
-        w[prefix + ".2.bias"] = rn(n, std=0.05)
+        w[prefix + ".2.bias"] = rn(n, std=0.5 * bias_std)
 
     n = dims.n_audio_state
     w["encoder.conv1.weight"] = rn(n, dims.n_mels, 3, std=1.0 / math.sqrt(dims.n_mels * 3))
@@ -112,7 +113,7 @@ def synth_weights(dims: Dims, seed: int = 11, dtype=torch.float16, eot_boost: fl
         ln(p + ".attn_ln", n)
         attn(p + ".attn", n, dims.n_text_head)
         ln(p + ".cross_attn_ln", n)
-        attn(p + ".cross_attn", n, dims.n_text_head)
+        attn(p + ".cross_attn", n, dims.n_text_head, gain=cross_gain)
         ln(p + ".mlp_ln", n)
         mlp(p + ".mlp", n)
     ln("decoder.ln", n)
