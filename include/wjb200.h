@@ -127,8 +127,9 @@ int wjb_profile_read(float* ms_by_class, int* launches_by_class, int n_classes);
  * `TenVad.process` loop at backends/ten.py:232-239): audio -> per-window speech probability.
  * Architecture and weight layout: see whisperjav_b200/vad.py.  probs fp32 [n_clips][n_windows]. */
 size_t wjb_vad_weights_bytes(void);
+size_t wjb_vad_workspace_bytes(int n_clips, int n_windows);
 int wjb_vad_forward(const float* audio, int64_t audio_stride, const int32_t* n_samples, int n_clips, const void* weights,
-                    float* probs, int n_windows, void* stream);
+                    float* probs, int n_windows, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

