@@ -5,7 +5,7 @@
 
 One *step* = one pass of the ASR hot path over one batch of synthetic speech-shaped 30 s windows:
 fused log-mel -> Whisper encoder -> cross-K/V projection -> greedy decode with the logit filters
-(timestamps mode, until every row hits EOT or sample_len), synthetic seeded weights of the exact
+(no-timestamps prefix as on the HF/anime path, until every row hits EOT or sample_len), synthetic seeded weights of the exact
 architecture (no checkpoints offline).  ``value`` times the step with the audio already resident in
 HBM; ``e2e`` times the public API (``WhisperB200.transcribe_batch``) from pinned host audio to result
 dicts on the host.  Under torchrun each rank runs its own batch (weak scaling, windows are independent)
@@ -130,7 +130,10 @@ def run_ours(args):
     host_audio = torch.stack([torch.from_numpy(c) for c in clips]).pin_memory()
     dev_audio = host_audio.cuda()
     ns = torch.full((B,), host_audio.shape[1], dtype=torch.int32, device="cuda")
-    dec_kw = dict(language="ja", task="transcribe", without_timestamps=False, max_initial_timestamp=0.0)
+    # HF / anime-path decode mode (forced <sot><ja><transcribe><notimestamps>): every 30 s clip is exactly one window in
+    # both the resident and the end-to-end arm (in timestamp mode the seek loop re-decodes clip tails at data-dependent
+    # offsets, which would make the two arms do different amounts of work); timestamp rules are covered by the parity tests
+    dec_kw = dict(language="ja", task="transcribe", without_timestamps=True)
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     def step_resident():
@@ -235,7 +238,7 @@ def run_ours(args):
     gemm_tf = enc_gemm_flops(dims, B) / (gemm_ms / 1e3) / 1e12
     attn_tf = enc_attn_flops(dims, B) / (attn_ms / 1e3) / 1e12
     steps_run = float(np.mean([x["steps_run"] for x in extra]))
-    n_initial = 3
+    n_initial = 4
     active = float(np.mean([sum(min(len(r.tokens) + 1 + (n_initial - 1), x["steps_run"]) for r in x["res"]) for x in extra]))
     dec_ms = float(np.mean(stage["decode"]))
     dec_gbs = decode_bytes(dims, steps_run, active, B) / (dec_ms / 1e3) / 1e9
@@ -266,7 +269,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic (seeded speech-shaped 16 kHz audio; seeded random-init weights of the exact architecture)",
-            "config": {"workload": f"whisper-{args.model} full hot path: log-mel + encoder + cross-KV + greedy decode (timestamps mode, to EOT/sample_len), "
+            "config": {"workload": f"whisper-{args.model} full hot path: log-mel + encoder + cross-KV + greedy decode (no-timestamps prefix, logit filters on, to EOT/sample_len), "
                                    f"batch {B} x 30 s windows per GPU", "global_batch": world * B, "parallelism": f"dp{world} (windows sharded, weights replicated)",
                        "l2": "L2 flushed (256 MiB write) between timed iterations; activations/weights also exceed L2",
                        "decode_tokens_per_step": tokens_out, "decoder_steps": steps_run},
@@ -295,15 +298,67 @@ def _cpu_window(model_name, sample_len, pw=None, dims=None, seed_audio=2000):
     mel = wo.pad_or_trim(wo.log_mel_spectrogram(a, dims.n_mels, padding=wo.N_SAMPLES)[:, : len(a) // 160], wo.N_FRAMES)
     xa = wo.encoder_forward(pw, dims, mel[None], True)
     t1 = time.time()
-    res = wo.decode(pw, dims, None, wo.DecodingOptions(language="ja", max_initial_timestamp=0.0, sample_len=sample_len), True, audio_features=xa)
+    res = wo.decode(pw, dims, None, wo.DecodingOptions(language="ja", without_timestamps=True, sample_len=sample_len), True, audio_features=xa)
     t2 = time.time()
     return t1 - t0, t2 - t1, len(res[0].tokens)
 
 
+def effective_cores() -> int:
+    """Cores this process may actually use: min(cpu_count, affinity mask, cgroup cpu.max quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def pick_threads() -> int:
+    """A short fp32 GEMM calibration over a few thread counts (shared hosts oversubscribe badly at
+    ``os.cpu_count()``); returns the fastest."""
+    cores = effective_cores()
+    cands = sorted({c for c in (cores, cores // 2, 64, 32, 16, 8) if 1 <= c <= cores})
+    a = torch.randn(1536, 1536)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        a @ a
+        t0 = time.time()
+        for _ in range(3):
+            a @ a
+        dt = time.time() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
+_THREADS = None
+
+
+def _cpu_token_time(pw, dims) -> float:
+    """Seconds per decoder token on the host (two cached steps on a dummy encoder output)."""
+    from oracle import whisper_oracle as wo
+    xa = torch.zeros(1, dims.n_audio_ctx, dims.n_audio_state)
+    st = wo.DecoderState()
+    wo.decoder_forward(pw, dims, torch.tensor([[50258, 50266, 50360]]), xa, st, True)
+    t0 = time.time()
+    for _ in range(2):
+        wo.decoder_forward(pw, dims, torch.tensor([[50365]]), xa, st, True)
+    return (time.time() - t0) / 2
+
+
 def _cpu_setup(model_name):
+    global _THREADS
     from oracle import whisper_oracle as wo
     from whisperjav_b200.synth import DIMS, synth_weights
-    torch.set_num_threads(os.cpu_count() or 1)
+    _THREADS = pick_threads()
     dims = DIMS[model_name]
     pw = wo.prepare_weights(synth_weights(dims, seed=11), True)
     return dims, pw
@@ -313,12 +368,11 @@ def cpu_baseline(model_name, budget_s=25.0):
     """The oracle (CPU restatement of the reference's openai-whisper path) timed on the host cores on a
     bounded sample: one 30 s window, decode capped so the whole thing stays near ``budget_s``."""
     dims, pw = _cpu_setup(model_name)
-    enc_s, dec_s, ntok = _cpu_window(model_name, 8, pw, dims)
-    per_tok = dec_s / max(ntok, 1)
-    cap = int(max(8, min(224, (budget_s - enc_s) / max(per_tok, 1e-3))))
+    per_tok = _cpu_token_time(pw, dims)
+    cap = int(max(4, min(224, (budget_s * 0.6) / max(per_tok, 1e-3))))
     enc_s, dec_s, ntok = _cpu_window(model_name, cap, pw, dims)
     wall = enc_s + dec_s
-    return {"value": WINDOW_S / wall, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": WINDOW_S / wall, "unit": "audio-s/s", "cores": _THREADS, "host_cpu_count": os.cpu_count(), "kind": "port",
             "sample": f"1 window of 30 s, whisper-{model_name}: mel+encoder {enc_s:.1f} s, greedy decode capped at {cap} tokens "
                       f"({ntok} produced, {dec_s:.1f} s); batch 1 per call as the reference runs it; torch CPU fp32 with fp16 rounding points",
             "note": "restated CPU path of openai-whisper @ c0d2f62 on synthetic weights (reference packages not installable offline); baseline only"}
@@ -329,10 +383,9 @@ def run_reference(args):
     if rank != 0:
         return
     dims, pw = _cpu_setup(args.model)
-    enc_s, dec_s, ntok = _cpu_window(args.model, 4, pw, dims)
-    per_tok = dec_s / max(ntok, 1)
-    per_step_budget = 170.0 / max(1, args.steps + args.warmup)
-    cap = int(max(4, min(224, (per_step_budget - enc_s) / max(per_tok, 1e-3))))
+    per_tok = _cpu_token_time(pw, dims)
+    per_step_budget = 150.0 / max(1, args.steps + args.warmup)
+    cap = int(max(2, min(224, (per_step_budget * 0.5) / max(per_tok, 1e-3))))
     for i in range(args.warmup):
         _cpu_window(args.model, cap, pw, dims, 2000 + i)
     t0 = time.time()
@@ -342,7 +395,7 @@ def run_reference(args):
         toks += n
     wall = time.time() - t0
     value = args.steps * WINDOW_S / wall
-    cb = {"value": value, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+    cb = {"value": value, "unit": "audio-s/s", "cores": _THREADS, "host_cpu_count": os.cpu_count(), "kind": "port",
           "sample": f"{args.steps} steps x 1 window of 30 s (batch 1 per call, as the reference does), greedy decode capped at {cap} tokens per window"}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),

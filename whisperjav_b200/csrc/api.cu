@@ -384,6 +384,7 @@ int wjb_encoder_forward(wjb_model* m, const void* mel_tm, int batch, void* out, 
         q.out = o;
         q.out_row_stride = N;
         q.flags = flags;
+        ProfScope ps(PC_GEMM, s);
         return launch_gemm(q, s);
     };
     auto ln = [&](const __half* x, const __half* g_, const __half* b_, __half* o) {

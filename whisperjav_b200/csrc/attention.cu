@@ -34,10 +34,10 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
     uint64_t* k_full = bars + 1;   // [2]
     uint64_t* k_empty = bars + 3;  // [2]
     uint64_t* v_full = bars + 5;
-    uint64_t* v_empty = bars + 6;
+    uint64_t* pv_done = bars + 6;  // PV_j finished: V stage free, P tile free, O accumulator up to date
     uint64_t* s_full = bars + 7;
-    uint64_t* p_full = bars + 8;
-    uint64_t* o_full = bars + 9;
+    uint64_t* s_free = bars + 8;   // softmax warps hold S_j in registers: TMEM S may be overwritten
+    uint64_t* p_full = bars + 9;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -51,10 +51,10 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
             mbar_init(&k_empty[i], 1);
         }
         mbar_init(v_full, 1);
-        mbar_init(v_empty, 1);
+        mbar_init(pv_done, 1);
         mbar_init(s_full, 1);
+        mbar_init(s_free, 128);
         mbar_init(p_full, 128);
-        mbar_init(o_full, 1);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -76,7 +76,7 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
                 mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
                 mbar_arrive_expect_tx(&k_full[st], kTileBytes);
                 tma_load_3d(sK + st * kTileBytes, &tmQKV, &k_full[st], n_state + h * kHeadDim, j * kKVTile, b);
-                mbar_wait(v_empty, (j & 1) ^ 1);
+                mbar_wait(pv_done, (j & 1) ^ 1);  // PV_{j-1} done -> V stage free
                 mbar_arrive_expect_tx(v_full, kTileBytes);
                 tma_load_3d(sV, &tmQKV, v_full, 2 * n_state + h * kHeadDim, j * kKVTile, b);
             }
@@ -84,30 +84,36 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);  // S = Q K^T, both K-major
-            constexpr uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);   // O = P V, V is MN-major
+            constexpr uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);   // O += P V, V is MN-major
             mbar_wait(q_full, 0);
             const uint64_t dq = make_smem_desc(smem_u32(sQ), 16, 1024, kLayoutSW128);
-            for (int j = 0; j < nkv; ++j) {
-                const int st = j & 1;
-                mbar_wait(&k_full[st], (j >> 1) & 1);
-                tc_fence_after();
-                const uint64_t dk = make_smem_desc(smem_u32(sK + st * kTileBytes), 16, 1024, kLayoutSW128);
+            // software pipeline: S_j is issued one block ahead of PV_{j-1}
+            for (int j = 0; j <= nkv; ++j) {
+                if (j < nkv) {
+                    const int st = j & 1;
+                    mbar_wait(&k_full[st], (j >> 1) & 1);
+                    if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+                    tc_fence_after();
+                    const uint64_t dk = make_smem_desc(smem_u32(sK + st * kTileBytes), 16, 1024, kLayoutSW128);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-                umma_commit(s_full);
-                umma_commit(&k_empty[st]);
-                mbar_wait(p_full, j & 1);
-                mbar_wait(v_full, j & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    // A: P k-block (k / 4), 32 B per 16 keys inside the 128 B row.  B: V rows 16*k.. (128 B per key row).
-                    const uint64_t dp = make_smem_desc(smem_u32(sP + (k >> 2) * kTileBytes) + (k & 3) * 32, 16, 1024, kLayoutSW128);
-                    const uint64_t dv = make_smem_desc(smem_u32(sV) + k * 16 * 128, 1024, 1024, kLayoutSW128);
-                    umma_f16(tmem_O, dp, dv, idesc_o, k != 0);
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                    umma_commit(s_full);
+                    umma_commit(&k_empty[st]);
                 }
-                umma_commit(o_full);
-                umma_commit(v_empty);
+                if (j > 0) {
+                    const int jj = j - 1;
+                    mbar_wait(p_full, jj & 1);
+                    mbar_wait(v_full, jj & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        // A: P k-block (k / 4), 32 B per 16 keys inside the 128 B row.  B: V rows 16*k.. (128 B per key row).
+                        const uint64_t dp = make_smem_desc(smem_u32(sP + (k >> 2) * kTileBytes) + (k & 3) * 32, 16, 1024, kLayoutSW128);
+                        const uint64_t dv = make_smem_desc(smem_u32(sV) + k * 16 * 128, 1024, 1024, kLayoutSW128);
+                        umma_f16(tmem_O, dp, dv, idesc_o, (jj | k) != 0);
+                    }
+                    umma_commit(pv_done);
+                }
             }
         }
     } else {
@@ -116,80 +122,78 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
         const int row = quad * 32 + lane;
         const uint32_t lane_off = uint32_t(quad * 32) << 16;
         const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-        float m = -INFINITY, l = 0.f;
-        float O[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) O[i] = 0.f;
+        float m_ref = -INFINITY, l = 0.f;                // m_ref: the max the accumulated O and l are scaled to
 
         for (int j = 0; j < nkv; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            if (j > 0) {
-                mbar_wait(o_full, (j - 1) & 1);
-                tc_fence_after();
+            uint32_t s[128];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_O + lane_off + c * 32, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(r[i]);
-                }
-            }
-            const int kvalid = T - j * kKVTile;  // keys >= kvalid are padding
-            // pass 1: row max
+            for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_S + lane_off + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);
+            const int kvalid = T - j * kKVTile;  // keys >= kvalid are padding (only in the last block)
             float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_S + lane_off + c * 32, r);
-                tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float s = __uint_as_float(r[i]);
-                    if (c * 32 + i < kvalid) mx = fmaxf(mx, s);
+            for (int i = 0; i < 128; ++i) {
+                if (i < kvalid) mx = fmaxf(mx, __uint_as_float(s[i]));
+            }
+            bool pv_waited = false;
+            if (j == 0) {
+                m_ref = mx;
+            } else {
+                // lazy rescale: keep the old reference max unless the new one is more than 2^8 above it
+                const bool need = (mx - m_ref) * sl2 > 8.0f;
+                if (__any_sync(0xffffffffu, need)) {
+                    mbar_wait(pv_done, (j - 1) & 1);
+                    tc_fence_after();
+                    pv_waited = true;
+                    const float alpha = need ? ex2_approx((m_ref - mx) * sl2) : 1.0f;
+                    if (need) m_ref = mx;
+                    l *= alpha;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t o[32];
+                        tmem_ld_32x32(tmem_O + lane_off + c * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_32x32(tmem_O + lane_off + c * 32, o);
+                    }
+                    tmem_st_wait();
                 }
             }
-            const float m_new = fmaxf(m, mx);
-            const float alpha = exp2f((m - m_new) * sl2);  // m = -inf on the first block -> 0
-            l *= alpha;
-#pragma unroll
-            for (int i = 0; i < 64; ++i) O[i] *= alpha;
-            m = m_new;
-            const float mb = m_new * sl2;
-            // pass 2: p = exp2(s*sl2 - m*sl2) -> fp16 -> swizzled smem
+            const float mb = m_ref * sl2;
             float lsum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_S + lane_off + c * 32, r);
-                tmem_ld_wait();
-                uint32_t packed[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float p0 = exp2f(fmaf(__uint_as_float(r[2 * i]), sl2, -mb));
-                    float p1 = exp2f(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mb));
-                    if (c * 32 + 2 * i >= kvalid) p0 = 0.f;
-                    if (c * 32 + 2 * i + 1 >= kvalid) p1 = 0.f;
-                    lsum += p0 + p1;
-                    __half2 hp = __floats2half2_rn(p0, p1);
-                    packed[i] = *reinterpret_cast<uint32_t*>(&hp);
-                }
-                // keys [c*32, c*32+32) -> k-block c/2, 16-byte chunks (c&1)*4 .. +4 of this row
+            for (int i = 0; i < 64; ++i) {
+                float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sl2, -mb));
+                float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -mb));
+                if (2 * i >= kvalid) p0 = 0.f;
+                if (2 * i + 1 >= kvalid) p1 = 0.f;
+                lsum += p0 + p1;
+                __half2 hp = __floats2half2_rn(p0, p1);
+                s[i] = *reinterpret_cast<uint32_t*>(&hp);
+            }
+            l += lsum;
+            if (j > 0 && !pv_waited) mbar_wait(pv_done, (j - 1) & 1);  // P tile is free once PV_{j-1} has read it
+            // keys [c*32, c*32+32) -> k-block c/2, 16-byte chunks (c&1)*4 .. +4 of this row (SWIZZLE_128B pattern)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
                 uint8_t* prow = sP + (c >> 1) * kTileBytes + row * 128;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
                     *reinterpret_cast<uint4*>(prow + chunk * 16) =
-                        make_uint4(packed[q4 * 4], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
+                        make_uint4(s[c * 16 + q4 * 4], s[c * 16 + q4 * 4 + 1], s[c * 16 + q4 * 4 + 2], s[c * 16 + q4 * 4 + 3]);
                 }
             }
-            l += lsum;
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(p_full);
         }
-        mbar_wait(o_full, (nkv - 1) & 1);
+        mbar_wait(pv_done, (nkv - 1) & 1);
         tc_fence_after();
         const float inv_l = 1.0f / l;
         const bool row_ok = q0 + row < T;
@@ -207,8 +211,7 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int idx = q4 * 8 + 2 * i;
-                        oh[i] = __floats2half2_rn((O[c * 32 + idx] + __uint_as_float(r[idx])) * inv_l,
-                                                  (O[c * 32 + idx + 1] + __uint_as_float(r[idx + 1])) * inv_l);
+                        oh[i] = __floats2half2_rn(__uint_as_float(r[idx]) * inv_l, __uint_as_float(r[idx + 1]) * inv_l);
                     }
                     *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = o;
                 }
