@@ -499,6 +499,8 @@ static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B
         q.out_row_stride = out_stride;
         q.flags = flags;
         q.block_n = 64;
+        if (B <= 64 && K % 32 == 0 && !getenv("WJB_DECODE_TC_GEMM"))
+            return launch_gemm_skinny(A, K, W, ldw, bias, res, out, (int)out_stride, B, N, K, flags, s);
         return launch_gemm(q, s);
     };
     if (int e = launch_embed(tokens, o.tokens_stride, m->h16("dec.emb"), m->h16("dec.pos"), w.x, w.ctl, B, n, s)) return e;
@@ -654,6 +656,11 @@ int wjb_profile_read(float* ms_by_class, int* launches_by_class, int n_classes) 
 int wjb_gemm_f16(const void* A, int64_t a_row_stride, int64_t a_batch_stride, int rows_per_batch, int n_batch, int K, const void* W,
                  int N, int ldw, const void* bias, const void* residual, void* out, int64_t out_row_stride, int64_t out_batch_stride,
                  int flags, int block_n, void* stream) {
+    if (block_n == -1) {  // weight-streaming variant (decoder steps)
+        if (n_batch != 1) return set_error("gemm: skinny variant needs n_batch == 1");
+        return launch_gemm_skinny((const __half*)A, (int)a_row_stride, (const __half*)W, ldw, (const __half*)bias, (const __half*)residual,
+                                  (__half*)out, (int)out_row_stride, rows_per_batch, N, K, flags & GEMM_GELU, (cudaStream_t)stream);
+    }
     GemmArgs g;
     g.A = (const __half*)A;
     g.a_row_stride = a_row_stride;

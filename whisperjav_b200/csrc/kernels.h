@@ -38,6 +38,9 @@ struct GemmArgs {
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 int gemm_init();  // set kernel attributes up front (outside any stream capture)
+// weight-streaming variant for <= 64 activation rows (decoder steps), gemm_skinny.cu
+int launch_gemm_skinny(const __half* x, int ldx, const __half* W, int ldw, const __half* bias, const __half* residual, __half* out,
+                       int ld_out, int M, int N, int K, int flags, cudaStream_t s);
 
 // ---- elementwise / normalisation (elementwise.cu) ------------------------------------------
 int launch_layernorm(const __half* x, const __half* gamma, const __half* beta, __half* out, int rows, int n, cudaStream_t s);
