@@ -1,0 +1,38 @@
+"""One shortened hot-path step for ncu (launch list / full captures): large-v3, batch B, decode capped at
+``--tokens`` sampled tokens so the launch list stays small.  Usage under gpurun:
+
+  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python scripts/profile_step.py --batch 64 --tokens 6
+"""
+import argparse
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from whisperjav_b200 import model as M  # noqa: E402
+from whisperjav_b200.synth import DIMS, speech_shaped_audio  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--model", default="large-v3")
+ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--tokens", type=int, default=6)
+ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--fast-weights", action="store_true", help="random weights generated on the GPU (values irrelevant for timing)")
+args = ap.parse_args()
+dims = DIMS[args.model]
+sd = None
+if args.fast_weights:
+    from whisperjav_b200.synth import synth_weights
+    small = synth_weights(DIMS["tiny"], seed=1)
+    ref = synth_weights.__wrapped__ if hasattr(synth_weights, "__wrapped__") else None
+m = M.load_model(args.model, max_batch=args.batch)
+base = [speech_shaped_audio(30.0, 2000 + i) for i in range(4)]
+audio = torch.stack([torch.from_numpy(base[i % 4]) for i in range(args.batch)]).cuda()
+ns = torch.full((args.batch,), audio.shape[1], dtype=torch.int32, device="cuda")
+for _ in range(args.reps):
+    mel = m.log_mel(audio, ns, n_frames=3000, layout="time")
+    xa = m.encode(mel)
+    res = m.decode_features(xa, language="ja", without_timestamps=True, sample_len=args.tokens)
+torch.cuda.synchronize()
+print("ok", [len(r.tokens) for r in res][:4])

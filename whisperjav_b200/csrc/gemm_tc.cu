@@ -168,10 +168,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + ch * kColsPerWarp;
 #pragma unroll 1
             for (int c = 0; c < kColsPerWarp; c += 32) {
+                const int col0 = nt * BN + ch * kColsPerWarp + c;
+                // residual for the (row, 8-column piece) slots this lane will own after the transpose: issue the loads
+                // before the TMEM read so their latency hides behind it
+                uint4 resv[4];
+                if (p.residual && col0 < p.N) {
+                    const int piece_ = lane & 3, colp_ = col0 + piece_ * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int grow_ = row_base + (lane >> 2) + 8 * i;
+                        resv[i] = make_uint4(0, 0, 0, 0);
+                        if (grow_ < p.rows_per_batch && colp_ + 8 <= p.N) {
+                            const long long off_ = (long long)b * p.out_batch_stride + (long long)grow_ * p.out_row_stride + colp_;
+                            resv[i] = *reinterpret_cast<const uint4*>(p.residual + off_);
+                        }
+                    }
+                }
                 uint32_t r[32];
                 tmem_ld_32x32(taddr0 + c, r);
                 tmem_ld_wait();
-                const int col0 = nt * BN + ch * kColsPerWarp + c;
                 if (col0 < p.N) {  // warp-uniform
                     // ---- this thread's row, 32 columns: bias, fp16 rounding, GELU (reference rounding points)
                     float v[32];
@@ -193,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (p.flags & GEMM_GELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(round_f16(v[j]));
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(round_f16(v[j]));
                     }
                     // ---- transpose through smem so that global accesses are 64 B contiguous per row
 #pragma unroll
@@ -237,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     for (int j = 0; j < 8; ++j) f[j] = round_f16(f[j]);
                                 }
                                 if (p.residual) {
-                                    uint4 rv = *reinterpret_cast<const uint4*>(p.residual + off);
+                                    const uint4 rv = resv[i];
                                     const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
                                     for (int j = 0; j < 4; ++j) {
