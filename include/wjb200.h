@@ -111,6 +111,9 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
 int wjb_gemm_f16(const void* A, int64_t a_row_stride, int64_t a_batch_stride, int rows_per_batch, int n_batch, int K,
                  const void* W, int N, int ldw, const void* bias, const void* residual, void* out, int64_t out_row_stride,
                  int64_t out_batch_stride, int flags, int block_n, void* stream);
+/* tuning hook for the decode-step GEMM: columns per CTA = 8*nt (nt 1|2|4), ks = K slices per column group (cluster size);
+ * 0 = built-in heuristic */
+void wjb_gemm_skinny_config(int nt, int ks);
 int wjb_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int n, void* stream);
 int wjb_attention_encoder_f16(const void* qkv, void* out, int batch, int T, int n_head, void* stream);
 /* single decoder step pieces */

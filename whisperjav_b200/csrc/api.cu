@@ -681,6 +681,8 @@ int wjb_gemm_f16(const void* A, int64_t a_row_stride, int64_t a_batch_stride, in
     return launch_gemm(g, (cudaStream_t)stream);
 }
 
+void wjb_gemm_skinny_config(int nt, int ks) { skinny_config(nt, ks); }
+
 int wjb_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int n, void* stream) {
     return launch_layernorm((const __half*)x, (const __half*)gamma, (const __half*)beta, (__half*)out, rows, n, (cudaStream_t)stream);
 }

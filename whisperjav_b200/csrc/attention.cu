@@ -18,9 +18,8 @@ namespace wjb {
 constexpr int kAttnThreads = 192;
 constexpr int kQTile = 128, kKVTile = 128, kHeadDim = 64;
 constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB
-constexpr int kOnesBytes = 2 * 16 * 128;  // [2 k-blocks][16 rows][64 halfs] of 1.0: B operand that makes the MMA produce row sums
-constexpr int kAttnSmem = 1024 + kTileBytes /*Q*/ + 2 * kTileBytes /*K*/ + kTileBytes /*V*/ + 2 * kTileBytes /*P*/ + kOnesBytes + 256;
-constexpr int kAttnTmemCols = 256;  // S: [0,128), O: [128,192), row sums l (16 identical columns): [192,208)
+constexpr int kAttnSmem = 1024 + kTileBytes /*Q*/ + 2 * kTileBytes /*K*/ + kTileBytes /*V*/ + 2 * kTileBytes /*P*/ + 256;
+constexpr int kAttnTmemCols = 256;  // S: [0,128), O: [128,192)
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int T, int n_state) {
@@ -30,8 +29,7 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
     uint8_t* sK = sQ + kTileBytes;       // 2 stages
     uint8_t* sV = sK + 2 * kTileBytes;
     uint8_t* sP = sV + kTileBytes;       // 2 k-blocks of [128 rows][64 keys]
-    uint8_t* sOnes = sP + 2 * kTileBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kOnesBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileBytes);
     uint64_t* q_full = bars + 0;
     uint64_t* k_full = bars + 1;   // [2]
     uint64_t* k_empty = bars + 3;  // [2]
@@ -63,17 +61,11 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
         if (lane == 0) tma_prefetch_desc(&tmQKV);
         tmem_alloc<kAttnTmemCols>(tmem_slot);
     }
-    if (warp >= 2) {  // all-ones tile (swizzle-invariant), read by the tensor core through the async proxy
-        const int t = threadIdx.x - 64;
-        reinterpret_cast<uint4*>(sOnes)[t * 2] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
-        reinterpret_cast<uint4*>(sOnes)[t * 2 + 1] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
-        fence_proxy_async();
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_L = tmem_base + 192;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -93,7 +85,6 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);  // S = Q K^T, both K-major
             constexpr uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);   // O += P V, V is MN-major
-            constexpr uint32_t idesc_l = make_idesc_f16(128, 16, 0, 0);   // l += P 1  (row sums of exactly the fp16 P that multiplies V)
             mbar_wait(q_full, 0);
             const uint64_t dq = make_smem_desc(smem_u32(sQ), 16, 1024, kLayoutSW128);
             // software pipeline: S_j is issued one block ahead of PV_{j-1}
@@ -120,8 +111,6 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
                         const uint64_t dp = make_smem_desc(smem_u32(sP + (k >> 2) * kTileBytes) + (k & 3) * 32, 16, 1024, kLayoutSW128);
                         const uint64_t dv = make_smem_desc(smem_u32(sV) + k * 16 * 128, 1024, 1024, kLayoutSW128);
                         umma_f16(tmem_O, dp, dv, idesc_o, (jj | k) != 0);
-                        const uint64_t d1 = make_smem_desc(smem_u32(sOnes + (k >> 2) * (16 * 128)) + (k & 3) * 32, 16, 1024, kLayoutSW128);
-                        umma_f16(tmem_L, dp, d1, idesc_l, (jj | k) != 0);
                     }
                     umma_commit(pv_done);
                 }
@@ -133,76 +122,93 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
         const int row = quad * 32 + lane;
         const uint32_t lane_off = uint32_t(quad * 32) << 16;
         const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-        float m_ref = -INFINITY;                         // the max the accumulated O and l are scaled to
+        float m_ref = -INFINITY, l = 0.f;                // m_ref: the max the accumulated O, l and P are scaled to
 
         for (int j = 0; j < nkv; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            uint32_t s[128];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_S + lane_off + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(s_free);
             const int kvalid = T - j * kKVTile;  // keys >= kvalid are padding (only possible in the last block)
-            if (kvalid < kKVTile) {
+            uint32_t pk[2][32];                   // fp16x2 P of the two 64-key halves
+            bool pv_waited = (j == 0);
+            // The block is consumed in two 64-key halves so that only 64 scores are live at a time.  The reference max
+            // is lazy: it only moves when a half's max exceeds it by more than 2^8; then O, l and any P already packed
+            // for this block are rescaled (rare after the first block).
 #pragma unroll
-                for (int i = 0; i < 128; ++i)
-                    if (i >= kvalid) s[i] = 0xff800000u;  // -inf: exp2 -> 0
-            }
-            float mx = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-            bool pv_waited = false;
-            if (j == 0) {
-                m_ref = mx;
-            } else {
-                // lazy rescale: keep the old reference max unless the new one is more than 2^8 above it
-                const bool need = (mx - m_ref) * sl2 > 8.0f;
-                if (__any_sync(0xffffffffu, need)) {
-                    mbar_wait(pv_done, (j - 1) & 1);
-                    tc_fence_after();
-                    pv_waited = true;
-                    const float alpha = need ? ex2_approx((m_ref - mx) * sl2) : 1.0f;
-                    if (need) m_ref = mx;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t o[32];
-                        tmem_ld_32x32(tmem_O + lane_off + c * 32, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st_32x32(tmem_O + lane_off + c * 32, o);
-                    }
-                    {
-                        uint32_t o[16];
-                        tmem_ld_32x16(tmem_L + lane_off, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st_32x16(tmem_L + lane_off, o);
-                    }
-                    tmem_st_wait();
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t s[64];
+                tmem_ld_32x32(tmem_S + lane_off + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+                tmem_ld_32x32(tmem_S + lane_off + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+                tmem_ld_wait();
+                if (hf == 1) {
+                    tc_fence_before();
+                    mbar_arrive(s_free);  // S_j fully read: the tensor core may overwrite it with S_{j+1}
                 }
+                if (kvalid < kKVTile) {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i)
+                        if (hf * 64 + i >= kvalid) s[i] = 0xff800000u;  // -inf: exp2 -> 0
+                }
+                float mx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+                if (j == 0 && hf == 0) {
+                    m_ref = mx;
+                } else {
+                    const bool need = (mx - m_ref) * sl2 > 8.0f;
+                    if (__any_sync(0xffffffffu, need)) {
+                        if (!pv_waited) {
+                            mbar_wait(pv_done, (j - 1) & 1);
+                            tc_fence_after();
+                            pv_waited = true;
+                        }
+                        const float alpha = need ? ex2_approx((m_ref - mx) * sl2) : 1.0f;
+                        if (need) m_ref = mx;
+                        l *= alpha;
+                        if (j > 0) {
+#pragma unroll 1
+                            for (int c = 0; c < 4; ++c) {
+                                uint32_t o[16];
+                                tmem_ld_32x16(tmem_O + lane_off + c * 16, o);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                                tmem_st_32x16(tmem_O + lane_off + c * 16, o);
+                            }
+                            tmem_st_wait();
+                        }
+                        if (hf == 1) {
+                            const __half2 a2 = __float2half2_rn(alpha);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                __half2 v = *reinterpret_cast<__half2*>(&pk[0][i]);
+                                v = __hmul2(v, a2);
+                                pk[0][i] = *reinterpret_cast<uint32_t*>(&v);
+                            }
+                        }
+                    }
+                }
+                const float mb = m_ref * sl2;
+                float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sl2, -mb));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -mb));
+                    ls0 += p0;
+                    ls1 += p1;
+                    __half2 hp = __floats2half2_rn(p0, p1);
+                    pk[hf][i] = *reinterpret_cast<uint32_t*>(&hp);
+                }
+                l += ls0 + ls1;
             }
-            const float mb = m_ref * sl2;
+            if (!pv_waited) mbar_wait(pv_done, (j - 1) & 1);  // P tile is free once PV_{j-1} has read it
+            // half hf = k-block hf of the P tile; 16-byte chunk q of this row goes to slot q ^ (row & 7) (SWIZZLE_128B)
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sl2, -mb));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -mb));
-                __half2 hp = __floats2half2_rn(p0, p1);
-                s[i] = *reinterpret_cast<uint32_t*>(&hp);
-            }
-            if (j > 0 && !pv_waited) mbar_wait(pv_done, (j - 1) & 1);  // P tile is free once PV_{j-1} has read it
-            // keys [c*32, c*32+32) -> k-block c/2, 16-byte chunks (c&1)*4 .. +4 of this row (SWIZZLE_128B pattern)
+            for (int hf = 0; hf < 2; ++hf) {
+                uint8_t* prow = sP + hf * kTileBytes + row * 128;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint8_t* prow = sP + (c >> 1) * kTileBytes + row * 128;
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(prow + chunk * 16) =
-                        make_uint4(s[c * 16 + q4 * 4], s[c * 16 + q4 * 4 + 1], s[c * 16 + q4 * 4 + 2], s[c * 16 + q4 * 4 + 3]);
+                for (int q = 0; q < 8; ++q) {
+                    const int chunk = q ^ (row & 7);
+                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[hf][q * 4], pk[hf][q * 4 + 1], pk[hf][q * 4 + 2], pk[hf][q * 4 + 3]);
                 }
             }
             fence_proxy_async();
@@ -211,13 +217,7 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
         }
         mbar_wait(pv_done, (nkv - 1) & 1);
         tc_fence_after();
-        float inv_l;
-        {
-            uint32_t lr[16];
-            tmem_ld_32x16(tmem_L + lane_off, lr);
-            tmem_ld_wait();
-            inv_l = 1.0f / __uint_as_float(lr[0]);
-        }
+        const float inv_l = 1.0f / l;
         const bool row_ok = q0 + row < T;
         __half* orow = out + ((long long)b * T + q0 + row) * n_state + h * kHeadDim;
 #pragma unroll

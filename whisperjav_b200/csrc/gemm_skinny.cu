@@ -211,34 +211,47 @@ static int launch_cfg(const SkinnyArgs& a, int groups, cudaStream_t s) {
     return 0;
 }
 
+static int g_force_nt = 0, g_force_ks = 0;  // tuning overrides (wjb_gemm_skinny_config); 0 = heuristic
+void skinny_config(int nt, int ks) {
+    g_force_nt = nt;
+    g_force_ks = ks;
+}
+
 int launch_gemm_skinny(const __half* x, int ldx, const __half* W, int ldw, const __half* bias, const __half* residual, __half* out,
                        int ld_out, int M, int N, int K, int flags, cudaStream_t s) {
     if (M < 1 || M > kSkMaxM) return set_error("gemm_skinny: M=%d out of range (1..64)", M);
     if (K % 32 || ldx % 8 || ldw % 8) return set_error("gemm_skinny: K %% 32, ldx %% 8, ldw %% 8 required");
     SkinnyArgs a{x, W, bias, residual, out, M, N, K, ldx, ldw, ld_out, flags, 1};
-    const int nt = (N >= 512) ? 4 : 1;
-    const int groups = (N + 8 * nt - 1) / (8 * nt);
     const int nkb = K / 32;
+    // column tile: 16 columns per CTA keeps ~80 registers/thread (3 CTAs/SM); K slices (cluster size) are added only
+    // while every CTA still fits in one wave and keeps >= 8 k blocks
+    int nt = g_force_nt ? g_force_nt : (N >= 256 ? 2 : 1);
+    int groups = (N + 8 * nt - 1) / (8 * nt);
     int ks = 1;
-    while (ks < 8 && groups * ks < sm_count() && nkb / (ks * 2) >= 4) ks *= 2;
+    if (g_force_ks) {
+        ks = g_force_ks;
+    } else {
+        const int slots = sm_count() * (nt == 4 ? 1 : 3);
+        while (ks < 8 && groups * ks * 2 <= slots && nkb / (ks * 2) >= 8) ks *= 2;
+    }
     a.ks = ks;
     const int mt = (M + 15) / 16;
 #define WJB_SK(MT_, NT_) return launch_cfg<MT_, NT_>(a, groups, s)
-    if (nt == 4) {
-        switch (mt) {
-            case 1: WJB_SK(1, 4);
-            case 2: WJB_SK(2, 4);
-            case 3: WJB_SK(3, 4);
-            default: WJB_SK(4, 4);
-        }
-    } else {
-        switch (mt) {
-            case 1: WJB_SK(1, 1);
-            case 2: WJB_SK(2, 1);
-            case 3: WJB_SK(3, 1);
-            default: WJB_SK(4, 1);
-        }
+#define WJB_SK_MT(NT_)           \
+    switch (mt) {                \
+        case 1: WJB_SK(1, NT_);  \
+        case 2: WJB_SK(2, NT_);  \
+        case 3: WJB_SK(3, NT_);  \
+        default: WJB_SK(4, NT_); \
     }
+    if (nt == 4) {
+        WJB_SK_MT(4)
+    } else if (nt == 2) {
+        WJB_SK_MT(2)
+    } else {
+        WJB_SK_MT(1)
+    }
+#undef WJB_SK_MT
 #undef WJB_SK
 }
 

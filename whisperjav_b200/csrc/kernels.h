@@ -42,6 +42,8 @@ int gemm_init();  // set kernel attributes up front (outside any stream capture)
 int launch_gemm_skinny(const __half* x, int ldx, const __half* W, int ldw, const __half* bias, const __half* residual, __half* out,
                        int ld_out, int M, int N, int K, int flags, cudaStream_t s);
 
+void skinny_config(int nt, int ks);
+
 // ---- elementwise / normalisation (elementwise.cu) ------------------------------------------
 int launch_layernorm(const __half* x, const __half* gamma, const __half* beta, __half* out, int rows, int n, cudaStream_t s);
 int launch_im2col_k3(const __half* xpad, __half* out, int B, int T_out, int C, int stride, int T_in_padded, cudaStream_t s);

@@ -319,8 +319,18 @@ class WhisperB200:
         for st in state:
             st["reset"] = 0
 
+        import os, time
+        _trace = os.environ.get("WJB_TIMING") == "1"
+        _t = {"t0": time.perf_counter()}
+
+        def _mark(name):
+            if _trace:
+                torch.cuda.synchronize()
+                _t[name] = time.perf_counter()
+
         # clip-level log-mel (content frames only), computed once per clip batch
         mels = self._clip_mels(arrs, content, pinned_audio)
+        _mark("mel")
 
         while True:
             active = [i for i in range(n) if state[i]["seek"] < content[i]]
@@ -330,12 +340,21 @@ class WhisperB200:
                 chunk = active[c0: c0 + self.max_batch]
                 sizes = [min(N_FRAMES, content[i] - state[i]["seek"]) for i in chunk]
                 win = self._gather_windows(mels, chunk, [state[i]["seek"] for i in chunk], sizes)
+                _mark("gather")
                 xa = self.encode(win)
+                _mark("encode")
                 prompts = [state[i]["all_tokens"][state[i]["reset"]:] for i in chunk]
                 results = self._decode_with_prompts(xa, prompts, temps[0], language, task, decode_options)
+                _mark("decode")
                 for j, i in enumerate(chunk):
                     self._advance(state[i], results[j], tok, sizes[j], no_speech_threshold, logprob_threshold,
                                   condition_on_previous_text)
+                _mark("advance")
+        if _trace:
+            import sys
+            keys = list(_t)
+            print("wjb timing (ms):", {k: round((_t[k] - _t[keys[max(0, keys.index(k) - 1)]]) * 1e3, 1) for k in keys[1:]},
+                  "passes", self.stats["device_passes"], file=sys.stderr)
         outs = []
         for i in range(n):
             toks = state[i]["all_tokens"][init_len:]
