@@ -46,7 +46,7 @@ for name, (N, K) in shapes.items():
             res[name][f"nt{nt}_ks{ks}"] = round(e0.elapsed_time(e1) / reps * 1000, 2)  # us
     # the tcgen05 kernel with BN=64 for comparison
     def g():
-        _lib.check(lib.wjb_gemm_f16(_lib.ptr(A), K, 0, M, 1, K, _lib.ptr(W), N, K, _lib.ptr(b), None, _lib.ptr(out), ld, 0, 0, 64, _lib.stream_ptr()), "tc")
+        _lib.check(lib.wjb_gemm_f16(_lib.ptr(A), K, 0, M, 1, K, _lib.ptr(W), N, K, _lib.ptr(b) if N % 32 == 0 else None, None, _lib.ptr(out), ld, 0, 0, 64, _lib.stream_ptr()), "tc")
     for _ in range(3):
         g()
     torch.cuda.synchronize()

@@ -190,6 +190,10 @@ struct wjb_model {
     int* h_done = nullptr;  // pinned
     cudaStream_t own_stream = nullptr;  // decode runs here (the caller's stream may be the legacy stream, which cannot be captured)
     cudaEvent_t ev = nullptr;
+    static constexpr int kMaxSplit = 8;
+    cudaStream_t br_stream[kMaxSplit] = {};   // decode branches (batch slices) run concurrently inside the step graph
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit] = {};
+    int g_split = 0;
     const __half* h16(const std::string& name) const { return reinterpret_cast<const __half*>(blob + L.off(name)); }
     const float* f32(const std::string& name) const { return reinterpret_cast<const float*>(blob + L.off(name)); }
 };
@@ -245,6 +249,11 @@ int wjb_model_create(const wjb_dims* dims, const void* weights_blob, wjb_model**
         delete m;
         return set_error("stream/event creation failed");
     }
+    cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < wjb_model::kMaxSplit; ++i) {
+        cudaStreamCreateWithFlags(&m->br_stream[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming);
+    }
     *out = m;
     return 0;
 }
@@ -255,6 +264,11 @@ void wjb_model_destroy(wjb_model* m) {
     if (m->h_done) cudaFreeHost(m->h_done);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->ev) cudaEventDestroy(m->ev);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    for (int i = 0; i < wjb_model::kMaxSplit; ++i) {
+        if (m->br_stream[i]) cudaStreamDestroy(m->br_stream[i]);
+        if (m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
+    }
     delete m;
 }
 
@@ -478,10 +492,24 @@ size_t wjb_decode_workspace_bytes(const wjb_model* m, int batch) {
     return dec_ws(m->d, batch, nullptr).total;
 }
 
-static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B, const wjb_decode_opts& o,
-                       const uint8_t* suppress_mask, int32_t* tokens, float* slp, float* nsp, int32_t* out_len, cudaStream_t s) {
+// One decoder step for the batch rows [b0, b0 + B) of a run over Btot rows, on stream s.
+static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, int Btot, int b0, int B, const wjb_decode_opts& o,
+                         const uint8_t* suppress_mask, int32_t* tokens0, float* slp0, float* nsp0, int32_t* out_len0, cudaStream_t s) {
     const wjb_dims& d = m->d;
     const int n = d.n_text_state, H = d.n_text_head, T = d.n_audio_ctx;
+    DecWs w = w0;  // row-offset views of the shared workspace
+    w.x += (size_t)b0 * n;
+    w.h += (size_t)b0 * n;
+    w.qkv += (size_t)b0 * 3 * n;
+    w.q += (size_t)b0 * n;
+    w.a += (size_t)b0 * n;
+    w.mlp += (size_t)b0 * 4 * n;
+    w.logits += (size_t)b0 * w.logits_stride;
+    w.done += b0;
+    int32_t* tokens = tokens0 + (size_t)b0 * o.tokens_stride;
+    float* slp = slp0 + b0;
+    float* nsp = nsp0 + b0;
+    int32_t* out_len = out_len0 + b0;
     auto linear = [&](const __half* A, int K, const __half* W, int ldw, const __half* bias, const __half* res, __half* out, int N,
                       long long out_stride, int flags) {
         GemmArgs q;
@@ -504,17 +532,17 @@ static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B
         return launch_gemm(q, s);
     };
     if (int e = launch_embed(tokens, o.tokens_stride, m->h16("dec.emb"), m->h16("dec.pos"), w.x, w.ctl, B, n, s)) return e;
-    const size_t self_per_layer = (size_t)B * 2 * H * d.n_text_ctx * 64;
-    const size_t cross_per_layer = (size_t)B * 2 * H * T * 64;
+    const size_t self_per_layer = (size_t)Btot * 2 * H * d.n_text_ctx * 64, self_row = (size_t)2 * H * d.n_text_ctx * 64;
+    const size_t cross_per_layer = (size_t)Btot * 2 * H * T * 64, cross_row = (size_t)2 * H * T * 64;
     for (int i = 0; i < d.n_text_layer; ++i) {
         const std::string p = "dec." + std::to_string(i) + ".";
         if (int e = launch_layernorm(w.x, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"), w.h, B, n, s)) return e;
         if (int e = linear(w.h, n, m->h16(p + "qkv.w"), n, m->h16(p + "qkv.b"), nullptr, w.qkv, 3 * n, 3 * n, 0)) return e;
-        if (int e = launch_attn_dec_self(w.qkv, w.self_kv + i * self_per_layer, w.a, &w.ctl->step, w.done, B, H, d.n_text_ctx, s)) return e;
+        if (int e = launch_attn_dec_self(w.qkv, w.self_kv + i * self_per_layer + b0 * self_row, w.a, &w.ctl->step, w.done, B, H, d.n_text_ctx, s)) return e;
         if (int e = linear(w.a, n, m->h16(p + "out.w"), n, m->h16(p + "out.b"), w.x, w.x, n, n, 0)) return e;
         if (int e = launch_layernorm(w.x, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"), w.h, B, n, s)) return e;
         if (int e = linear(w.h, n, m->h16(p + "cq.w"), n, m->h16(p + "cq.b"), nullptr, w.q, n, n, 0)) return e;
-        if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv) + i * cross_per_layer, w.a, w.done, B, H, T, s))
+        if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv0) + i * cross_per_layer + b0 * cross_row, w.a, w.done, B, H, T, s))
             return e;
         if (int e = linear(w.a, n, m->h16(p + "cout.w"), n, m->h16(p + "cout.b"), w.x, w.x, n, n, 0)) return e;
         if (int e = launch_layernorm(w.x, m->h16(p + "ln3.g"), m->h16(p + "ln3.b"), w.h, B, n, s)) return e;
@@ -538,6 +566,31 @@ static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B
     p.n_ctx = d.n_text_ctx;
     p.tokens_stride = o.tokens_stride;
     return launch_sample(w.logits, suppress_mask, tokens, nullptr, slp, nsp, out_len, w.done, w.ctl, p, s);
+}
+
+// Fork the step into `split` batch slices on their own streams (captured as parallel graph branches): the
+// latency-bound weight GEMMs of one slice overlap the HBM-bound cross-attention of another.
+static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B, const wjb_decode_opts& o,
+                       const uint8_t* suppress_mask, int32_t* tokens, float* slp, float* nsp, int32_t* out_len, cudaStream_t s, int split) {
+    if (split > B) split = B;
+    if (split <= 1) {
+        if (int e = decode_branch(m, w, cross_kv, B, 0, B, o, suppress_mask, tokens, slp, nsp, out_len, s)) return e;
+        return launch_advance(w.ctl, s);
+    }
+    cudaEventRecord(m->ev_fork, s);
+    int rc = 0;
+    for (int i = 0; i < split; ++i) {
+        const int b0 = (int)((long long)B * i / split), b1 = (int)((long long)B * (i + 1) / split);
+        cudaStream_t bs = (i == 0) ? s : m->br_stream[i];
+        if (i > 0) cudaStreamWaitEvent(bs, m->ev_fork, 0);
+        if (!rc) rc = decode_branch(m, w, cross_kv, B, b0, b1 - b0, o, suppress_mask, tokens, slp, nsp, out_len, bs);
+        if (i > 0) {
+            cudaEventRecord(m->ev_join[i], bs);
+            cudaStreamWaitEvent(s, m->ev_join[i], 0);
+        }
+    }
+    if (rc) return rc;
+    return launch_advance(w.ctl, s);
 }
 
 int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_decode_opts* opts, const uint8_t* suppress_mask,
@@ -574,10 +627,14 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
     cudaMemsetAsync(out_len, 0, sizeof(int32_t) * batch, s);
     // h_ctl lives on this stack frame: make sure the copy has been consumed before we return
     const bool use_graph = getenv("WJB_NO_GRAPH") == nullptr;
+    int split = 4;
+    if (const char* e = getenv("WJB_DECODE_SPLIT")) split = atoi(e);
+    if (split < 1) split = 1;
+    if (split > wjb_model::kMaxSplit) split = wjb_model::kMaxSplit;
     if (use_graph) {
         const bool hit = m->graph && m->g_kv == cross_kv && m->g_ws == workspace && m->g_B == batch && m->g_mask == suppress_mask &&
                          m->g_tokens == tokens && m->g_slp == sum_logprob && m->g_nsp == no_speech_prob && m->g_len == out_len &&
-                         memcmp(&m->g_opts, &o, sizeof(o)) == 0;
+                         m->g_split == split && memcmp(&m->g_opts, &o, sizeof(o)) == 0;
         if (!hit) {
             if (m->graph) {
                 cudaGraphExecDestroy(m->graph);
@@ -587,7 +644,7 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
             cudaGraph_t graph = nullptr;
             if ((ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
                 return set_error("decode: begin capture: %s", cudaGetErrorString(ce));
-            int e = decode_step(m, w, cross_kv, batch, o, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, s);
+            int e = decode_step(m, w, cross_kv, batch, o, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, s, split);
             ce = cudaStreamEndCapture(s, &graph);
             if (e) {
                 if (graph) cudaGraphDestroy(graph);
@@ -606,6 +663,7 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
             m->g_nsp = no_speech_prob;
             m->g_len = out_len;
             m->g_opts = o;
+            m->g_split = split;
         }
     }
     const int check_every = o.check_every > 0 ? o.check_every : 8;
@@ -614,7 +672,7 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
         if (use_graph) {
             if ((ce = cudaGraphLaunch(m->graph, s)) != cudaSuccess) return set_error("decode: graph launch: %s", cudaGetErrorString(ce));
         } else {
-            if (int e = decode_step(m, w, cross_kv, batch, o, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, s)) return e;
+            if (int e = decode_step(m, w, cross_kv, batch, o, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, s, split)) return e;
         }
         if ((step + 1) % check_every == 0 && step + 1 >= o.n_initial) {
             cudaMemcpyAsync(m->h_done, &w.ctl->n_done, sizeof(int), cudaMemcpyDeviceToHost, s);

@@ -216,6 +216,10 @@ int launch_sample(const __half* logits, const unsigned char* suppress_mask, int*
     if (smem > 110 * 1024) return set_error("sample: vocab %d too large", p.n_vocab);
     sample_kernel<<<p.B, kSampleThreads, smem, s>>>(logits, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, done, ctl, p);
     WJB_CHECK_LAUNCH("sample");
+    return 0;
+}
+
+int launch_advance(DecodeCtl* ctl, cudaStream_t s) {
     advance_kernel<<<1, 1, 0, s>>>(ctl);
     WJB_CHECK_LAUNCH("advance");
     return 0;

@@ -223,17 +223,12 @@ int launch_gemm_skinny(const __half* x, int ldx, const __half* W, int ldw, const
     if (K % 32 || ldx % 8 || ldw % 8) return set_error("gemm_skinny: K %% 32, ldx %% 8, ldw %% 8 required");
     SkinnyArgs a{x, W, bias, residual, out, M, N, K, ldx, ldw, ld_out, flags, 1};
     const int nkb = K / 32;
-    // column tile: 16 columns per CTA keeps ~80 registers/thread (3 CTAs/SM); K slices (cluster size) are added only
-    // while every CTA still fits in one wave and keeps >= 8 k blocks
-    int nt = g_force_nt ? g_force_nt : (N >= 256 ? 2 : 1);
+    // measured on B200 (scripts/skinny_sweep.py): cluster launches cost more than they save except for the long-K fc2;
+    // 8 columns per CTA for <= 16 rows (x slice is small), 16 otherwise
+    const int mt_ = (M + 15) / 16;
+    int nt = g_force_nt ? g_force_nt : ((mt_ >= 2 && N >= 256) ? 2 : 1);
     int groups = (N + 8 * nt - 1) / (8 * nt);
-    int ks = 1;
-    if (g_force_ks) {
-        ks = g_force_ks;
-    } else {
-        const int slots = sm_count() * (nt == 4 ? 1 : 3);
-        while (ks < 8 && groups * ks * 2 <= slots && nkb / (ks * 2) >= 8) ks *= 2;
-    }
+    int ks = g_force_ks ? g_force_ks : ((nkb >= 128 && groups * 2 <= 3 * sm_count()) ? 2 : 1);
     a.ks = ks;
     const int mt = (M + 15) / 16;
 #define WJB_SK(MT_, NT_) return launch_cfg<MT_, NT_>(a, groups, s)

@@ -98,6 +98,8 @@ int launch_embed(const int* tokens, int tokens_stride, const __half* emb, const 
 int launch_sample(const __half* logits, const unsigned char* suppress_mask, int* tokens, const int* initial_tokens, float* sum_logprob,
                   float* no_speech_prob, int* out_len, unsigned char* done, DecodeCtl* ctl, const DecodeParams& p, cudaStream_t s);
 
+int launch_advance(DecodeCtl* ctl, cudaStream_t s);
+
 // ---- VAD (vad.cu) --------------------------------------------------------------------------
 struct VadArgs;
 }  // namespace wjb
