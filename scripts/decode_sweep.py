@@ -6,9 +6,10 @@ code = r'''
 import sys, time, torch, os
 sys.path.insert(0, %r)
 from whisperjav_b200 import model as M
+print("WJB_DECODE_MEGA =", os.environ.get("WJB_DECODE_MEGA"), flush=True)
 m = M.load_model("large-v3", max_batch=64)
 xa = torch.randn(64, 1500, 1280, device="cuda", dtype=torch.float16)
-for split, tc in [(1,0),(2,0),(4,0),(8,0),(1,1),(2,1),(4,1),(8,1)]:
+for split, tc in [(1,1),(4,0)]:
     os.environ["WJB_DECODE_SPLIT"] = str(split)
     if tc: os.environ["WJB_DECODE_TC_GEMM"] = "1"
     else: os.environ.pop("WJB_DECODE_TC_GEMM", None)

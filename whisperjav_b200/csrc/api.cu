@@ -460,6 +460,8 @@ struct DecWs {
     __half *x, *h, *qkv, *q, *a, *mlp, *logits, *self_kv;
     DecodeCtl* ctl;
     unsigned char* done;
+    MegaLayer* mega_layers;
+    unsigned* mega_bar;
     int logits_stride;
     size_t total;
 };
@@ -483,6 +485,8 @@ static DecWs dec_ws(const wjb_dims& d, int B, uint8_t* base) {
     w.self_kv = (__half*)take((size_t)d.n_text_layer * B * 2 * d.n_text_head * d.n_text_ctx * 64 * 2);
     w.ctl = (DecodeCtl*)take(sizeof(DecodeCtl));
     w.done = (unsigned char*)take((size_t)B);
+    w.mega_layers = (MegaLayer*)take(sizeof(MegaLayer) * d.n_text_layer);
+    w.mega_bar = (unsigned*)take(256);
     w.total = off;
     return w;
 }
@@ -572,6 +576,55 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
 // latency-bound weight GEMMs of one slice overlap the HBM-bound cross-attention of another.
 static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B, const wjb_decode_opts& o,
                        const uint8_t* suppress_mask, int32_t* tokens, float* slp, float* nsp, int32_t* out_len, cudaStream_t s, int split) {
+    static const bool use_mega = getenv("WJB_DECODE_MEGA") == nullptr || atoi(getenv("WJB_DECODE_MEGA")) != 0;
+    const wjb_dims& dm = m->d;
+    if (use_mega && B <= 64 && dm.n_text_state <= 1280 && dm.n_text_state % 32 == 0) {
+        MegaLaunch ml;
+        ml.layers = w.mega_layers;
+        ml.n_layer = dm.n_text_layer;
+        ml.emb = m->h16("dec.emb");
+        ml.pos = m->h16("dec.pos");
+        ml.lnf_g = m->h16("dec.ln.g");
+        ml.lnf_b = m->h16("dec.ln.b");
+        ml.B = B;
+        ml.n = dm.n_text_state;
+        ml.H = dm.n_text_head;
+        ml.T = dm.n_audio_ctx;
+        ml.n_ctx = dm.n_text_ctx;
+        ml.n_vocab = dm.n_vocab;
+        ml.logits_stride = w.logits_stride;
+        ml.x = w.x;
+        ml.h = w.h;
+        ml.qkv = w.qkv;
+        ml.q = w.q;
+        ml.a = w.a;
+        ml.mlp = w.mlp;
+        ml.logits = w.logits;
+        ml.self_kv = w.self_kv;
+        ml.cross_kv = reinterpret_cast<const __half*>(cross_kv);
+        ml.tokens = tokens;
+        ml.tokens_stride = o.tokens_stride;
+        ml.ctl = w.ctl;
+        ml.done = w.done;
+        ml.bar = w.mega_bar;
+        if (int e = launch_decode_mega(ml, s)) return e;
+        DecodeParams p;
+        p.B = B;
+        p.n_vocab = dm.n_vocab;
+        p.logits_stride = w.logits_stride;
+        p.eot = o.eot;
+        p.no_speech = o.no_speech;
+        p.no_timestamps = o.no_timestamps;
+        p.timestamp_begin = o.timestamp_begin;
+        p.suppress_blank = o.suppress_blank;
+        p.blank_token = o.blank_token;
+        p.apply_timestamp_rules = o.apply_timestamp_rules;
+        p.max_initial_timestamp_index = o.max_initial_timestamp_index;
+        p.n_ctx = dm.n_text_ctx;
+        p.tokens_stride = o.tokens_stride;
+        if (int e = launch_sample(w.logits, suppress_mask, tokens, nullptr, slp, nsp, out_len, w.done, w.ctl, p, s)) return e;
+        return launch_advance(w.ctl, s);
+    }
     if (split > B) split = B;
     if (split <= 1) {
         if (int e = decode_branch(m, w, cross_kv, B, 0, B, o, suppress_mask, tokens, slp, nsp, out_len, s)) return e;
@@ -621,6 +674,34 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
     cudaError_t ce;
     if ((ce = cudaMemcpyAsync(w.ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, s)) != cudaSuccess)
         return set_error("decode ctl copy: %s", cudaGetErrorString(ce));
+    {
+        std::vector<MegaLayer> tab(d.n_text_layer);
+        for (int i = 0; i < d.n_text_layer; ++i) {
+            const std::string p = "dec." + std::to_string(i) + ".";
+            MegaLayer& L = tab[i];
+            L.ln1_g = m->h16(p + "ln1.g");
+            L.ln1_b = m->h16(p + "ln1.b");
+            L.qkv_w = m->h16(p + "qkv.w");
+            L.qkv_b = m->h16(p + "qkv.b");
+            L.out_w = m->h16(p + "out.w");
+            L.out_b = m->h16(p + "out.b");
+            L.ln2_g = m->h16(p + "ln2.g");
+            L.ln2_b = m->h16(p + "ln2.b");
+            L.cq_w = m->h16(p + "cq.w");
+            L.cq_b = m->h16(p + "cq.b");
+            L.cout_w = m->h16(p + "cout.w");
+            L.cout_b = m->h16(p + "cout.b");
+            L.ln3_g = m->h16(p + "ln3.g");
+            L.ln3_b = m->h16(p + "ln3.b");
+            L.fc1_w = m->h16(p + "fc1.w");
+            L.fc1_b = m->h16(p + "fc1.b");
+            L.fc2_w = m->h16(p + "fc2.w");
+            L.fc2_b = m->h16(p + "fc2.b");
+        }
+        if ((ce = cudaMemcpyAsync(w.mega_layers, tab.data(), sizeof(MegaLayer) * tab.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+            return set_error("decode table copy: %s", cudaGetErrorString(ce));
+        cudaStreamSynchronize(s);  // tab is a stack-lifetime host buffer
+    }
     cudaMemsetAsync(w.done, 0, batch, s);
     cudaMemsetAsync(sum_logprob, 0, sizeof(float) * batch, s);
     cudaMemsetAsync(no_speech_prob, 0, sizeof(float) * batch, s);

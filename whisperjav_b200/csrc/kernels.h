@@ -100,6 +100,28 @@ int launch_sample(const __half* logits, const unsigned char* suppress_mask, int*
 
 int launch_advance(DecodeCtl* ctl, cudaStream_t s);
 
+// ---- persistent decoder-step kernel (decode_mega.cu) -----------------------------------------
+struct MegaLayer {  // device-resident table, one entry per decoder layer
+    const __half *ln1_g, *ln1_b, *qkv_w, *qkv_b, *out_w, *out_b;
+    const __half *ln2_g, *ln2_b, *cq_w, *cq_b, *cout_w, *cout_b;
+    const __half *ln3_g, *ln3_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+};
+struct MegaLaunch {
+    const MegaLayer* layers;  // device pointer
+    int n_layer;
+    const __half *emb, *pos, *lnf_g, *lnf_b;
+    int B, n, H, T, n_ctx, n_vocab, logits_stride;
+    __half *x, *h, *qkv, *q, *a, *mlp, *logits;
+    __half* self_kv;
+    const __half* cross_kv;
+    const int* tokens;
+    int tokens_stride;
+    const DecodeCtl* ctl;
+    const unsigned char* done;
+    unsigned* bar;  // device counter for the grid barrier
+};
+int launch_decode_mega(const MegaLaunch& m, cudaStream_t s);
+
 // ---- VAD (vad.cu) --------------------------------------------------------------------------
 struct VadArgs;
 }  // namespace wjb
