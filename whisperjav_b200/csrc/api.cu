@@ -462,6 +462,7 @@ struct DecWs {
     unsigned char* done;
     MegaLayer* mega_layers;
     unsigned* mega_bar;
+    unsigned long long* mega_prof;
     int logits_stride;
     size_t total;
 };
@@ -487,6 +488,7 @@ static DecWs dec_ws(const wjb_dims& d, int B, uint8_t* base) {
     w.done = (unsigned char*)take((size_t)B);
     w.mega_layers = (MegaLayer*)take(sizeof(MegaLayer) * d.n_text_layer);
     w.mega_bar = (unsigned*)take(256);
+    w.mega_prof = (unsigned long long*)take(8 * 1024);
     w.total = off;
     return w;
 }
@@ -607,6 +609,7 @@ static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B
         ml.ctl = w.ctl;
         ml.done = w.done;
         ml.bar = w.mega_bar;
+        ml.prof = getenv("WJB_MEGA_PROF") ? w.mega_prof : nullptr;
         if (int e = launch_decode_mega(ml, s)) return e;
         DecodeParams p;
         p.B = B;
@@ -765,6 +768,20 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
         }
     }
     if ((ce = cudaStreamSynchronize(s)) != cudaSuccess) return set_error("decode: final sync: %s", cudaGetErrorString(ce));
+    if (getenv("WJB_MEGA_PROF")) {
+        const int per_layer = 11, n_stamp = 2 + per_layer * d.n_text_layer + 2;
+        std::vector<unsigned long long> t(n_stamp);
+        cudaMemcpy(t.data(), w.mega_prof, sizeof(unsigned long long) * n_stamp, cudaMemcpyDeviceToHost);
+        const char* names[per_layer] = {"ln1", "qkv", "self", "out", "ln2", "cq", "cross", "cout", "ln3", "fc1", "fc2"};
+        double acc[per_layer] = {0};
+        for (int l = 0; l < d.n_text_layer; ++l)
+            for (int k = 0; k < per_layer; ++k) acc[k] += double(t[2 + l * per_layer + k] - t[1 + l * per_layer + k]) * 1e-3;
+        fprintf(stderr, "wjb mega profile (last step, us summed over layers): embed %.1f", double(t[1] - t[0]) * 1e-3);
+        for (int k = 0; k < per_layer; ++k) fprintf(stderr, " %s %.1f", names[k], acc[k]);
+        const int base = 1 + per_layer * d.n_text_layer;
+        fprintf(stderr, " lnf %.1f logits %.1f total %.1f\n", double(t[base + 1] - t[base]) * 1e-3, double(t[base + 2] - t[base + 1]) * 1e-3,
+                double(t[base + 2] - t[0]) * 1e-3);
+    }
     if (steps_run) *steps_run = step;
     return 0;
 }

@@ -25,7 +25,7 @@ constexpr int kMegaThreads = 256;
 
 struct MegaSmem {
     union {
-        float red[4][64][32];                 // GEMM partial tiles (32 KB)
+        float red[4][64][40];                 // GEMM partial tiles, up to 5 column tiles (40 KB)
         struct {
             float sc[2][1536];                // cross-attention scores per group
             float red2[2][8];
@@ -78,11 +78,11 @@ struct GemmPhase {
     int N, K, ld_out, flags;
 };
 
-// NT tiles (8 columns each) at once; each warp iteration covers U = 4 / NT k-blocks per tile so that four 16-byte weight
-// loads per lane are always in flight.
+// NT tiles (8 columns each) at once.  A warp iteration covers U k-blocks per tile (U = 2 for NT <= 2, else 1); weights AND activations of iteration it+1 are issued before the
+// MMAs of iteration it (register double buffering).
 template <int NT>
-__device__ __noinline__ void gemm_tiles(const GemmPhase& g, int B, const int (&tile)[4], MegaSmem& sm) {
-    constexpr int U = 4 / NT;
+__device__ __noinline__ void gemm_tiles(const GemmPhase& g, int B, const int (&tile)[5], MegaSmem& sm) {
+    constexpr int U = (NT <= 2) ? 2 : 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gq = lane >> 2, t4 = lane & 3;
     const int nkb = g.K / 32;
@@ -102,47 +102,55 @@ __device__ __noinline__ void gemm_tiles(const GemmPhase& g, int B, const int (&t
         n_ok[nt] = n < g.N;
         wrow[nt] = g.W + (size_t)(n_ok[nt] ? n : 0) * g.K + t4 * 8;
     }
+    const __half* arow[8];
+    bool a_ok[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = (i >> 1) * 16 + gq + 8 * (i & 1);
+        a_ok[i] = r < B;
+        arow[i] = g.A + (size_t)(a_ok[i] ? r : 0) * g.lda + t4 * 8;
+    }
     // iteration it of warp w covers k-blocks (it * 8 + w) * U + u, u < U
-    uint4 wv[NT][U], wn[NT][U];
-    auto wload = [&](uint4 (&dst)[NT][U], int it) {
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int kb = (it * 8 + warp) * U + u;
-                dst[nt][u] = (kb < nkb && n_ok[nt]) ? __ldg(reinterpret_cast<const uint4*>(wrow[nt] + (size_t)kb * 32)) : zero4;
-            }
-    };
-    const int n_it = (nkb + 8 * U - 1) / (8 * U);
-    wload(wv, 0);
-    for (int it = 0; it < n_it; ++it) {
-        if (it + 1 < n_it) wload(wn, it + 1);
+    uint4 wv[NT][U], wn[NT][U], xv[U][8], xn[U][8];
+    auto load_it = [&](uint4 (&wd)[NT][U], uint4 (&xd)[U][8], int it) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int kb = (it * 8 + warp) * U + u;
-            if (kb < nkb) {
-                const __half* ak = g.A + (size_t)kb * 32 + t4 * 8;
+            const bool k_ok = kb < nkb;
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
-                    const int r0 = mt * 16 + gq, r1 = r0 + 8;
-                    const uint4 x0 = (r0 < B) ? ldcg16(ak + (size_t)r0 * g.lda) : zero4;
-                    const uint4 x1 = (r1 < B) ? ldcg16(ak + (size_t)r1 * g.lda) : zero4;
+            for (int nt = 0; nt < NT; ++nt)
+                wd[nt][u] = (k_ok && n_ok[nt]) ? __ldg(reinterpret_cast<const uint4*>(wrow[nt] + (size_t)kb * 32)) : zero4;
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        mma16816(acc[mt][nt], x0.x, x1.x, x0.y, x1.y, wv[nt][u].x, wv[nt][u].y);
-                        mma16816(acc[mt][nt], x0.z, x1.z, x0.w, x1.w, wv[nt][u].z, wv[nt][u].w);
-                    }
+            for (int i = 0; i < 8; ++i) xd[u][i] = (k_ok && a_ok[i]) ? ldcg16(arow[i] + (size_t)kb * 32) : zero4;
+        }
+    };
+    const int n_it = (nkb + 8 * U - 1) / (8 * U);
+    load_it(wv, xv, 0);
+    for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) load_it(wn, xn, it + 1);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                const uint4 x0 = xv[u][2 * mt], x1 = xv[u][2 * mt + 1];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    mma16816(acc[mt][nt], x0.x, x1.x, x0.y, x1.y, wv[nt][u].x, wv[nt][u].y);
+                    mma16816(acc[mt][nt], x0.z, x1.z, x0.w, x1.w, wv[nt][u].z, wv[nt][u].w);
                 }
             }
         }
         if (it + 1 < n_it) {
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
+            for (int u = 0; u < U; ++u) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) wv[nt][u] = wn[nt][u];
+                for (int nt = 0; nt < NT; ++nt) wv[nt][u] = wn[nt][u];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xv[u][i] = xn[u][i];
+            }
         }
     }
-    // fixed-order tree over the 8 warps (deterministic)
+    // fixed-order tree over the 8 warps (deterministic); the final tile lands in sm.red[0]
     auto store_acc = [&](int slot) {
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
@@ -177,47 +185,58 @@ __device__ __noinline__ void gemm_tiles(const GemmPhase& g, int B, const int (&t
     __syncthreads();
     if (warp == 0) {
         add_acc(0);
+        store_acc(0);
+    }
+    __syncthreads();
+    // epilogue by all 256 threads: thread -> (row m, column pair); loads first, then math, then stores
+    constexpr int kPairs = NT * 4;              // column pairs per row
+    constexpr int kOut = 64 * kPairs;           // outputs handled per CTA
+    constexpr int kPer = (kOut + kMegaThreads - 1) / kMegaThreads;
+    float v0[kPer], v1[kPer], r0[kPer], r1[kPer], b0[kPer], b1[kPer];
+    size_t off[kPer];
+    int ok[kPer];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+    for (int i = 0; i < kPer; ++i) {
+        const int idx = threadIdx.x + i * kMegaThreads;
+        const int m = idx / kPairs, cp = idx % kPairs;
+        const int nt = cp >> 2, c0 = tile[nt < NT ? nt : 0] * 8 + (cp & 3) * 2;
+        ok[i] = 0;
+        r0[i] = r1[i] = b0[i] = b1[i] = 0.f;
+        off[i] = 0;
+        if (idx < kOut && m < B && c0 < g.N) {
+            ok[i] = (c0 + 1 < g.N) ? 2 : 1;
+            off[i] = (size_t)m * g.ld_out + c0;
+            const float2 t = *reinterpret_cast<const float2*>(&sm.red[0][m][nt * 8 + (cp & 3) * 2]);
+            v0[i] = t.x;
+            v1[i] = t.y;
+            if (g.bias) {
+                b0[i] = __half2float(__ldg(g.bias + c0));
+                if (ok[i] == 2) b1[i] = __half2float(__ldg(g.bias + c0 + 1));
+            }
+            if (g.residual) {
+                r0[i] = __half2float(__ldcg(g.residual + off[i]));
+                if (ok[i] == 2) r1[i] = __half2float(__ldcg(g.residual + off[i] + 1));
+            }
+        }
+    }
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int m = mt * 16 + gq + 8 * hf;
-                    const int c0 = tile[nt] * 8 + t4 * 2;
-                    if (m >= B || c0 >= g.N) continue;
-                    const bool two = (c0 + 1 < g.N);
-                    float v0 = acc[mt][nt][2 * hf], v1 = acc[mt][nt][2 * hf + 1];
-                    if (g.bias) {
-                        v0 += __half2float(__ldg(g.bias + c0));
-                        if (two) v1 += __half2float(__ldg(g.bias + c0 + 1));
-                    }
-                    v0 = round_f16(v0);
-                    v1 = round_f16(v1);
-                    if (g.flags & GEMM_GELU) {
-                        v0 = gelu_erf(v0);
-                        v1 = gelu_erf(v1);
-                    }
-                    const size_t off = (size_t)m * g.ld_out + c0;
-                    if (g.residual) {
-                        v0 = round_f16(v0);
-                        v1 = round_f16(v1);
-                        if (two && ((off & 1) == 0)) {
-                            const float2 r = __half22float2(__ldcg(reinterpret_cast<const __half2*>(g.residual + off)));
-                            v0 += r.x;
-                            v1 += r.y;
-                        } else {
-                            v0 += __half2float(__ldcg(g.residual + off));
-                            if (two) v1 += __half2float(__ldcg(g.residual + off + 1));
-                        }
-                    }
-                    if (two && ((off & 1) == 0)) {
-                        *reinterpret_cast<__half2*>(g.out + off) = __floats2half2_rn(v0, v1);
-                    } else {
-                        g.out[off] = __float2half_rn(v0);
-                        if (two) g.out[off + 1] = __float2half_rn(v1);
-                    }
-                }
+    for (int i = 0; i < kPer; ++i) {
+        if (!ok[i]) continue;
+        float a0 = round_f16(v0[i] + b0[i]), a1 = round_f16(v1[i] + b1[i]);
+        if (g.flags & GEMM_GELU) {
+            a0 = round_f16(gelu_erf(a0));
+            a1 = round_f16(gelu_erf(a1));
+        }
+        if (g.residual) {
+            a0 += r0[i];
+            a1 += r1[i];
+        }
+        if (ok[i] == 2 && ((off[i] & 1) == 0)) {
+            *reinterpret_cast<__half2*>(g.out + off[i]) = __floats2half2_rn(a0, a1);
+        } else {
+            g.out[off[i]] = __float2half_rn(a0);
+            if (ok[i] == 2) g.out[off[i] + 1] = __float2half_rn(a1);
+        }
     }
     __syncthreads();  // sm.red is reused by the next chunk
 }
@@ -225,22 +244,20 @@ __device__ __noinline__ void gemm_tiles(const GemmPhase& g, int B, const int (&t
 __device__ void gemm_phase(const GemmPhase& g, int B, MegaSmem& sm) {
     const int n_tiles = (g.N + 7) / 8;
     const int grid = gridDim.x;
-    // this CTA owns tiles blockIdx.x, blockIdx.x + grid, ...
+    // this CTA owns tiles blockIdx.x, blockIdx.x + grid, ...; up to 5 at once
     int t = blockIdx.x;
     while (t < n_tiles) {
-        int tile[4];
+        int tile[5] = {0, 0, 0, 0, 0};
         int cnt = 0;
-        for (; cnt < 4 && t < n_tiles; ++cnt, t += grid) tile[cnt] = t;
-        if (cnt == 4) {
-            gemm_tiles<4>(g, B, tile, sm);
-        } else if (cnt >= 2) {
-            gemm_tiles<2>(g, B, tile, sm);
-            if (cnt == 3) {
-                int t1[4] = {tile[2], 0, 0, 0};
-                gemm_tiles<1>(g, B, t1, sm);
-            }
-        } else {
-            gemm_tiles<1>(g, B, tile, sm);
+        const int remaining = (n_tiles - t + grid - 1) / grid;
+        const int take = remaining >= 8 ? 4 : (remaining > 5 ? (remaining + 1) / 2 : remaining);  // avoid a tiny last chunk
+        for (; cnt < take && cnt < 5 && t < n_tiles; ++cnt, t += grid) tile[cnt] = t;
+        switch (cnt) {
+            case 5: gemm_tiles<5>(g, B, tile, sm); break;
+            case 4: gemm_tiles<4>(g, B, tile, sm); break;
+            case 3: gemm_tiles<3>(g, B, tile, sm); break;
+            case 2: gemm_tiles<2>(g, B, tile, sm); break;
+            default: gemm_tiles<1>(g, B, tile, sm); break;
         }
     }
 }
@@ -387,7 +404,7 @@ __device__ __noinline__ void cross_attn_item(const __half* qh, const __half* Kh,
             qf[2 * j + 1] = f.y;
         }
     }
-    constexpr int UN = 8;  // 16-byte loads in flight per thread
+    constexpr int UN = 16;  // 16-byte loads in flight per thread
     for (int t0 = 0; t0 < T; t0 += 16 * UN) {
         uint4 u[UN];
 #pragma unroll
@@ -482,6 +499,7 @@ struct MegaArgs {
     const DecodeCtl* ctl;
     const unsigned char* done;
     unsigned* bar;
+    unsigned long long* prof;  // optional: globaltimer at every barrier exit of CTA 0 (debug)
 };
 
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const MegaArgs a) {
@@ -491,6 +509,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
     const int B = a.B, n = a.n, H = a.H;
     const int step = a.ctl->step;
     unsigned target = 0;
+    int prof_i = 0;
+    auto stamp = [&]() {
+        if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            a.prof[prof_i++] = t;
+        }
+    };
+    stamp();
 
     // ---- embedding: row b -> CTA b % grid (warp 0..): x = half(emb[tok] + pos[step])
     for (int b = blockIdx.x + grid * warp; b < B; b += grid * 8) {
@@ -504,6 +531,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
         }
     }
     grid_barrier(a.bar, target, grid);
+    stamp();
 
     const size_t self_row = (size_t)2 * H * a.n_ctx * 64, cross_row = (size_t)2 * H * a.T * 64;
     for (int l = 0; l < a.n_layer; ++l) {
@@ -513,11 +541,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
         // ---- self-attention block
         ln_phase(a.x, L.ln1_g, L.ln1_b, a.h, B, n);
         grid_barrier(a.bar, target, grid);
+    stamp();
         {
             GemmPhase g{a.h, n, L.qkv_w, L.qkv_b, nullptr, a.qkv, 3 * n, n, 3 * n, 0};
             gemm_phase(g, B, sm);
         }
         grid_barrier(a.bar, target, grid);
+    stamp();
         for (int item = blockIdx.x * 8 + warp; item < B * H; item += grid * 8) {
             const int b = item / H, hh = item % H;
             if (a.done[b]) continue;
@@ -530,19 +560,23 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
             self_attn_item(row + hh * 64, kc, vc, a.a + (size_t)b * n + hh * 64, step, sm.probs[warp]);
         }
         grid_barrier(a.bar, target, grid);
+    stamp();
         {
             GemmPhase g{a.a, n, L.out_w, L.out_b, a.x, a.x, n, n, n, 0};
             gemm_phase(g, B, sm);
         }
         grid_barrier(a.bar, target, grid);
+    stamp();
         // ---- cross-attention block
         ln_phase(a.x, L.ln2_g, L.ln2_b, a.h, B, n);
         grid_barrier(a.bar, target, grid);
+    stamp();
         {
             GemmPhase g{a.h, n, L.cq_w, L.cq_b, nullptr, a.q, n, n, n, 0};
             gemm_phase(g, B, sm);
         }
         grid_barrier(a.bar, target, grid);
+    stamp();
         {
             const int grp = threadIdx.x >> 7;
             for (int item = blockIdx.x * 2 + grp; item < B * H; item += grid * 2) {
@@ -553,31 +587,38 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
             }
         }
         grid_barrier(a.bar, target, grid);
+    stamp();
         {
             GemmPhase g{a.a, n, L.cout_w, L.cout_b, a.x, a.x, n, n, n, 0};
             gemm_phase(g, B, sm);
         }
         grid_barrier(a.bar, target, grid);
+    stamp();
         // ---- MLP block
         ln_phase(a.x, L.ln3_g, L.ln3_b, a.h, B, n);
         grid_barrier(a.bar, target, grid);
+    stamp();
         {
             GemmPhase g{a.h, n, L.fc1_w, L.fc1_b, nullptr, a.mlp, 4 * n, n, 4 * n, GEMM_GELU};
             gemm_phase(g, B, sm);
         }
         grid_barrier(a.bar, target, grid);
+    stamp();
         {
             GemmPhase g{a.mlp, 4 * n, L.fc2_w, L.fc2_b, a.x, a.x, n, 4 * n, n, 0};
             gemm_phase(g, B, sm);
         }
         grid_barrier(a.bar, target, grid);
+    stamp();
     }
     ln_phase(a.x, a.lnf_g, a.lnf_b, a.h, B, n);
     grid_barrier(a.bar, target, grid);
+    stamp();
     {
         GemmPhase g{a.h, n, a.emb, nullptr, nullptr, a.logits, a.n_vocab, n, a.logits_stride, 0};
         gemm_phase(g, B, sm);
     }
+    stamp();
 }
 
 int launch_decode_mega(const MegaLaunch& m, cudaStream_t s) {
@@ -611,6 +652,7 @@ int launch_decode_mega(const MegaLaunch& m, cudaStream_t s) {
     a.ctl = m.ctl;
     a.done = m.done;
     a.bar = m.bar;
+    a.prof = m.prof;
     cudaError_t e = cudaMemsetAsync(m.bar, 0, sizeof(unsigned), s);
     if (e != cudaSuccess) return set_error("decode_mega memset: %s", cudaGetErrorString(e));
     decode_mega_kernel<<<sm_count(), kMegaThreads, 0, s>>>(a);

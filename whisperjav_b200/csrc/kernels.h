@@ -119,6 +119,7 @@ struct MegaLaunch {
     const DecodeCtl* ctl;
     const unsigned char* done;
     unsigned* bar;  // device counter for the grid barrier
+    unsigned long long* prof;  // optional per-phase timestamps (debug), >= 512 entries
 };
 int launch_decode_mega(const MegaLaunch& m, cudaStream_t s);
 
