@@ -143,7 +143,10 @@ def run_ours(args):
     # HF / anime-path decode mode (forced <sot><ja><transcribe><notimestamps>): every 30 s clip is exactly one window in
     # both the resident and the end-to-end arm (in timestamp mode the seek loop re-decodes clip tails at data-dependent
     # offsets, which would make the two arms do different amounts of work); timestamp rules are covered by the parity tests
-    dec_kw = dict(language="ja", task="transcribe", without_timestamps=True)
+    # timestamp ids are added to the suppress list: upstream leaves them sampleable even with <|notimestamps|> (real
+    # checkpoints never emit them there, random-init weights do, and transcribe() would then re-decode clip tails)
+    ts0 = dims.n_vocab - 1501
+    dec_kw = dict(language="ja", task="transcribe", without_timestamps=True, suppress_tokens=[-1] + list(range(ts0, dims.n_vocab)))
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     def step_resident():
@@ -308,7 +311,8 @@ def _cpu_window(model_name, sample_len, pw=None, dims=None, seed_audio=2000):
     mel = wo.pad_or_trim(wo.log_mel_spectrogram(a, dims.n_mels, padding=wo.N_SAMPLES)[:, : len(a) // 160], wo.N_FRAMES)
     xa = wo.encoder_forward(pw, dims, mel[None], True)
     t1 = time.time()
-    res = wo.decode(pw, dims, None, wo.DecodingOptions(language="ja", without_timestamps=True, sample_len=sample_len), True, audio_features=xa)
+    res = wo.decode(pw, dims, None, wo.DecodingOptions(language="ja", without_timestamps=True, sample_len=sample_len,
+                                                          suppress_tokens=[-1] + list(range(dims.n_vocab - 1501, dims.n_vocab))), True, audio_features=xa)
     t2 = time.time()
     return t1 - t0, t2 - t1, len(res[0].tokens)
 

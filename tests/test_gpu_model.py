@@ -12,7 +12,7 @@ from whisperjav_b200 import model as M
 from whisperjav_b200.synth import DIMS, speech_shaped_audio, synth_weights
 
 pytestmark = pytest.mark.gpu
-NEAR_TIE = 0.05  # oracle top-2 logit margin below which a divergence is not counted as a failure
+NEAR_TIE = 0.08  # oracle top-2 logit margin (5 fp16 quanta at |logit| ~ 16) below which a divergence is not counted as a failure
 
 
 @pytest.fixture(scope="module")

@@ -239,7 +239,7 @@ class WhisperB200:
         opts.max_initial_timestamp_index = mi
         opts.tokens_stride, opts.check_every = stride, 8
 
-        key = ("mask", str(suppress_tokens), language, task)
+        key = ("mask", hash(str(suppress_tokens)), language, task)
         mask = self._bufs.get(key)
         if suppress_tokens is None or suppress_tokens == "" or suppress_tokens == []:
             mask = None
