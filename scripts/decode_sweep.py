@@ -9,10 +9,8 @@ from whisperjav_b200 import model as M
 print("WJB_DECODE_MEGA =", os.environ.get("WJB_DECODE_MEGA"), flush=True)
 m = M.load_model("large-v3", max_batch=64)
 xa = torch.randn(64, 1500, 1280, device="cuda", dtype=torch.float16)
-for split, tc in [(1,1),(4,0)]:
+for split, tc in [(1,1),(2,1)]:
     os.environ["WJB_DECODE_SPLIT"] = str(split)
-    if tc: os.environ["WJB_DECODE_TC_GEMM"] = "1"
-    else: os.environ.pop("WJB_DECODE_TC_GEMM", None)
     m.decode_features(xa, without_timestamps=True, sample_len=24)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     s0 = m.stats["decode_steps"]

@@ -31,7 +31,7 @@ def gemm(lib, A, W, bias=None, res=None, flags=0, block_n=0, rows_per_batch=None
 
 
 @pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 256), (128, 256, 256, 256), (256, 512, 128, 128), (1000, 1280, 1280, 0),
-                                      (64, 1280, 1280, 64), (3, 384, 384, 64), (130, 51866, 384, 0), (4096, 3840, 1280, 256)])
+                                      (64, 1280, 1280, 64), (64, 1280, 1280, 32), (16, 3840, 1280, 32), (64, 1280, 5120, 0), (3, 384, 384, 64), (130, 51866, 384, 0), (4096, 3840, 1280, 256)])
 def test_gemm_plain(lib, diag_dir, M, N, K, bn):
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
     A = (torch.randn(M, K, generator=g) * 0.5).half().to(DEV)

@@ -532,8 +532,9 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
         q.out = out;
         q.out_row_stride = out_stride;
         q.flags = flags;
-        q.block_n = 64;
-        if (B <= 64 && K % 32 == 0 && !getenv("WJB_DECODE_TC_GEMM"))
+        q.block_n = 0;  // auto: 32-wide tiles when that still leaves SMs idle, else 64
+        static const bool use_skinny = getenv("WJB_DECODE_SKINNY") != nullptr;
+        if (use_skinny && B <= 64 && K % 32 == 0)
             return launch_gemm_skinny(A, K, W, ldw, bias, res, out, (int)out_stride, B, N, K, flags, s);
         return launch_gemm(q, s);
     };
@@ -713,7 +714,7 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
     cudaMemsetAsync(out_len, 0, sizeof(int32_t) * batch, s);
     // h_ctl lives on this stack frame: make sure the copy has been consumed before we return
     const bool use_graph = getenv("WJB_NO_GRAPH") == nullptr;
-    int split = 4;
+    int split = 1;  // measured on B200: batch-slice branches only pay off with the mma.sync GEMM (WJB_DECODE_SKINNY)
     if (const char* e = getenv("WJB_DECODE_SPLIT")) split = atoi(e);
     if (split < 1) split = 1;
     if (split > wjb_model::kMaxSplit) split = wjb_model::kMaxSplit;

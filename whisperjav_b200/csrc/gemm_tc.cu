@@ -31,8 +31,9 @@ struct GemmCfg {
     static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
     static constexpr int kStageBytesB = BN * kBlockK * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 10));
     static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kEpiWarpsActive = (BN >= 64) ? kNumEpiWarps : 4;  // BN = 32: one 32-column chunk per lane quadrant
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kNumEpiWarps * 32 * kStgRowBytes;
 };
 
@@ -81,7 +82,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], kNumEpiWarps);
+            mbar_init(&tempty_bar[a], Cfg::kEpiWarpsActive);
         }
         fence_barrier_init();
     }
@@ -151,11 +152,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp >= kEpiWarp0) {
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + Cfg::kEpiWarpsActive) {
         // ===================== epilogue =====================
         const int q = warp & 3;                   // TMEM lane quadrant this warp may read
         const int ch = (warp - kEpiWarp0) >> 2;   // column half
-        constexpr int kColsPerWarp = BN / 2;
+        constexpr int kColsPerWarp = (BN >= 64) ? BN / 2 : BN;
         uint8_t* stg = stage_base + (warp - kEpiWarp0) * (32 * kStgRowBytes);
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -325,7 +326,8 @@ int gemm_init() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmemBytes)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes)) != cudaSuccess)
+        (e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<32>::kSmemBytes)) != cudaSuccess)
         return set_error("gemm_init: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -368,12 +370,14 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
         bn = 256;
         if (tiles_m * ((a.N + 255) / 256) < sm_count()) bn = 128;
         if (tiles_m * ((a.N + 127) / 128) < sm_count()) bn = 64;
+        if (tiles_m * ((a.N + 63) / 64) * 2 <= sm_count()) bn = 32;
     }
     const int tiles = tiles_m * ((a.N + bn - 1) / bn);
     switch (bn) {
         case 256: return launch_bn<256>(a, tmA, d, tiles, stream);
         case 128: return launch_bn<128>(a, tmA, d, tiles, stream);
         case 64: return launch_bn<64>(a, tmA, d, tiles, stream);
+        case 32: return launch_bn<32>(a, tmA, d, tiles, stream);
     }
     return set_error("gemm: unsupported block_n %d", bn);
 }
