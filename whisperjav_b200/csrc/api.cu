@@ -503,6 +503,8 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
                          const uint8_t* suppress_mask, int32_t* tokens0, float* slp0, float* nsp0, int32_t* out_len0, cudaStream_t s) {
     const wjb_dims& d = m->d;
     const int n = d.n_text_state, H = d.n_text_head, T = d.n_audio_ctx;
+    // debugging aid: WJB_DECODE_SKIP bit mask removes kernel classes from the step (1 LN, 2 GEMM, 4 self-attn, 8 cross-attn)
+    static const int skip = getenv("WJB_DECODE_SKIP") ? atoi(getenv("WJB_DECODE_SKIP")) : 0;
     DecWs w = w0;  // row-offset views of the shared workspace
     w.x += (size_t)b0 * n;
     w.h += (size_t)b0 * n;
@@ -533,6 +535,7 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
         q.out_row_stride = out_stride;
         q.flags = flags;
         q.block_n = 0;  // auto: 32-wide tiles when that still leaves SMs idle, else 64
+        if (skip & 2) return 0;
         static const bool use_skinny = getenv("WJB_DECODE_SKINNY") != nullptr;
         if (use_skinny && B <= 64 && K % 32 == 0)
             return launch_gemm_skinny(A, K, W, ldw, bias, res, out, (int)out_stride, B, N, K, flags, s);
@@ -543,20 +546,20 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
     const size_t cross_per_layer = (size_t)Btot * 2 * H * T * 64, cross_row = (size_t)2 * H * T * 64;
     for (int i = 0; i < d.n_text_layer; ++i) {
         const std::string p = "dec." + std::to_string(i) + ".";
-        if (int e = launch_layernorm(w.x, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"), w.h, B, n, s)) return e;
+        if (!(skip & 1)) if (int e = launch_layernorm(w.x, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"), w.h, B, n, s)) return e;
         if (int e = linear(w.h, n, m->h16(p + "qkv.w"), n, m->h16(p + "qkv.b"), nullptr, w.qkv, 3 * n, 3 * n, 0)) return e;
-        if (int e = launch_attn_dec_self(w.qkv, w.self_kv + i * self_per_layer + b0 * self_row, w.a, &w.ctl->step, w.done, B, H, d.n_text_ctx, s)) return e;
+        if (!(skip & 4)) if (int e = launch_attn_dec_self(w.qkv, w.self_kv + i * self_per_layer + b0 * self_row, w.a, &w.ctl->step, w.done, B, H, d.n_text_ctx, s)) return e;
         if (int e = linear(w.a, n, m->h16(p + "out.w"), n, m->h16(p + "out.b"), w.x, w.x, n, n, 0)) return e;
-        if (int e = launch_layernorm(w.x, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"), w.h, B, n, s)) return e;
+        if (!(skip & 1)) if (int e = launch_layernorm(w.x, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"), w.h, B, n, s)) return e;
         if (int e = linear(w.h, n, m->h16(p + "cq.w"), n, m->h16(p + "cq.b"), nullptr, w.q, n, n, 0)) return e;
-        if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv0) + i * cross_per_layer + b0 * cross_row, w.a, w.done, B, H, T, s))
+        if (!(skip & 8)) if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv0) + i * cross_per_layer + b0 * cross_row, w.a, w.done, B, H, T, s))
             return e;
         if (int e = linear(w.a, n, m->h16(p + "cout.w"), n, m->h16(p + "cout.b"), w.x, w.x, n, n, 0)) return e;
-        if (int e = launch_layernorm(w.x, m->h16(p + "ln3.g"), m->h16(p + "ln3.b"), w.h, B, n, s)) return e;
+        if (!(skip & 1)) if (int e = launch_layernorm(w.x, m->h16(p + "ln3.g"), m->h16(p + "ln3.b"), w.h, B, n, s)) return e;
         if (int e = linear(w.h, n, m->h16(p + "fc1.w"), n, m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, 4 * n, GEMM_GELU)) return e;
         if (int e = linear(w.mlp, 4 * n, m->h16(p + "fc2.w"), 4 * n, m->h16(p + "fc2.b"), w.x, w.x, n, n, 0)) return e;
     }
-    if (int e = launch_layernorm(w.x, m->h16("dec.ln.g"), m->h16("dec.ln.b"), w.h, B, n, s)) return e;
+    if (!(skip & 1)) if (int e = launch_layernorm(w.x, m->h16("dec.ln.g"), m->h16("dec.ln.b"), w.h, B, n, s)) return e;
     if (int e = linear(w.h, n, m->h16("dec.emb"), n, nullptr, nullptr, w.logits, d.n_vocab, w.logits_stride, 0)) return e;
     DecodeParams p;
     p.B = B;
