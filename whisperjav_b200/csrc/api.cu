@@ -47,6 +47,10 @@ tensor_map_encode_fn get_tensor_map_encoder() {
 
 int sample_init();
 
+static bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
+void set_pdl(bool on) { g_pdl = on; }
+
 // ---- optional per-kernel-class timing (CUDA events on the launching stream) -----------------
 enum { PC_GEMM = 0, PC_ATTN = 1, PC_LN = 2, PC_N = 3 };
 struct ProfRec {
@@ -734,7 +738,10 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
             cudaGraph_t graph = nullptr;
             if ((ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
                 return set_error("decode: begin capture: %s", cudaGetErrorString(ce));
+            static const bool want_pdl = getenv("WJB_NO_PDL") == nullptr;
+            set_pdl(want_pdl);
             int e = decode_step(m, w, cross_kv, batch, o, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, s, split);
+            set_pdl(false);
             ce = cudaStreamEndCapture(s, &graph);
             if (e) {
                 if (graph) cudaGraphDestroy(graph);

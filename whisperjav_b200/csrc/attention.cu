@@ -10,6 +10,8 @@
 //    openai-whisper model.py::MultiHeadAttention.qkv_attention.
 //  * attn_dec_self_kernel / attn_dec_cross_kernel: single-query decode attention against the HBM
 //    KV cache / the per-window cross K,V; pure streaming, HBM-bound (cross: 384 KB per (b, head)).
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace wjb {
@@ -278,6 +280,7 @@ int launch_attn_encoder(const __half* qkv, __half* out, int B, int T, int H, cud
 __global__ void __launch_bounds__(32) attn_dec_self_kernel(const __half* __restrict__ qkv, __half* __restrict__ kv_cache,
                                                            __half* __restrict__ out, const int* __restrict__ step_ptr,
                                                            const unsigned char* __restrict__ done, int H, int n_ctx) {
+    pdl_prologue();
     const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
     if (done && done[b]) return;
     const int pos = *step_ptr;
@@ -348,7 +351,7 @@ int launch_attn_dec_self(const __half* qkv, __half* kv_cache, __half* out, const
                          int n_ctx, cudaStream_t s) {
     if (n_ctx > 448) return set_error("attn_dec_self: n_ctx %d > 448", n_ctx);
     dim3 grid(H, B);
-    attn_dec_self_kernel<<<grid, 32, 0, s>>>(qkv, kv_cache, out, step, done, H, n_ctx);
+    launch_k(attn_dec_self_kernel, grid, dim3(32), 0, s, qkv, kv_cache, out, step, done, H, n_ctx);
     WJB_CHECK_LAUNCH("attn_dec_self");
     return 0;
 }
@@ -361,6 +364,7 @@ constexpr int kCrossMaxT = 1536;
 __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
                                                                         __half* __restrict__ out,
                                                                         const unsigned char* __restrict__ done, int H, int T) {
+    pdl_prologue();
     const int h = blockIdx.x, b = blockIdx.y;
     if (done && done[b]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -467,11 +471,156 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_kernel(const __h
     }
 }
 
+// ---- bulk-copy variant: K and V stream through a 4-stage smem ring filled by cp.async.bulk (one elected thread, mbarrier
+// completion), so the bytes in flight are not bounded by the LSU's outstanding-request capacity; V chunks are already in
+// flight while the softmax runs.
+constexpr int kCbStages = 4, kCbKeys = 128, kCbStageBytes = kCbKeys * 128;
+constexpr int kCbSmem = kCbStages * kCbStageBytes + kCrossMaxT * 4 + 64 * 4 + 4 * 64 * 4 + 64;
+
+__global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
+                                                                             __half* __restrict__ out,
+                                                                             const unsigned char* __restrict__ done, int H, int T) {
+    pdl_prologue();
+    const int h = blockIdx.x, b = blockIdx.y;
+    if (done && done[b]) return;
+    extern __shared__ __align__(128) uint8_t cb_smem[];
+    uint8_t* ring = cb_smem;
+    float* sc = reinterpret_cast<float*>(cb_smem + kCbStages * kCbStageBytes);
+    float* red = sc + kCrossMaxT;
+    float* osum = red + 64;                      // [4][64]
+    uint64_t* full = reinterpret_cast<uint64_t*>(osum + 4 * 64);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = H * 64;
+    const uint8_t* Kg = reinterpret_cast<const uint8_t*>(kv + ((long long)(b * 2 * H + h) * T) * 64);
+    const uint8_t* Vg = reinterpret_cast<const uint8_t*>(kv + ((long long)(b * 2 * H + H + h) * T) * 64);
+    const int nck = (T + kCbKeys - 1) / kCbKeys;  // chunks per matrix
+    const int total = 2 * nck;
+    auto chunk_src = [&](int c) { return (c < nck ? Kg : Vg) + (size_t)(c % nck) * kCbStageBytes; };
+    auto chunk_keys = [&](int c) { return min(kCbKeys, T - (c % nck) * kCbKeys); };
+    auto issue = [&](int c) {
+        const int st = c % kCbStages;
+        const uint32_t bytes = chunk_keys(c) * 128;
+        mbar_arrive_expect_tx(&full[st], bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(ring + st * kCbStageBytes)),
+                     "l"(chunk_src(c)), "r"(bytes), "r"(smem_u32(&full[st]))
+                     : "memory");
+    };
+    if (tid == 0) {
+        for (int i = 0; i < kCbStages; ++i) mbar_init(&full[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int c = 0; c < kCbStages && c < total; ++c) issue(c);
+
+    const int chunk16 = tid & 7, slot = tid >> 3;  // 16 key slots x 8 sixteen-byte pieces
+    float qf[8];
+    {
+        const uint4 u = reinterpret_cast<const uint4*>(q + (long long)b * n + h * 64)[chunk16];
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h2[j]);
+            qf[2 * j] = f.x;
+            qf[2 * j + 1] = f.y;
+        }
+    }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    float inv = 0.f;
+    for (int c = 0; c < total; ++c) {
+        const int st = c % kCbStages;
+        mbar_wait(&full[st], (c / kCbStages) & 1);
+        const uint8_t* base = ring + st * kCbStageBytes;
+        const int keys = chunk_keys(c);
+        const int key0 = (c % nck) * kCbKeys;
+        if (c < nck) {
+#pragma unroll
+            for (int it = 0; it < kCbKeys / 16; ++it) {
+                const int k = it * 16 + slot;
+                const uint4 u = *reinterpret_cast<const uint4*>(base + k * 128 + chunk16 * 16);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+                float s_ = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h2[j]);
+                    s_ = fmaf(qf[2 * j], f.x, s_);
+                    s_ = fmaf(qf[2 * j + 1], f.y, s_);
+                }
+                s_ += __shfl_xor_sync(0xffffffffu, s_, 1);
+                s_ += __shfl_xor_sync(0xffffffffu, s_, 2);
+                s_ += __shfl_xor_sync(0xffffffffu, s_, 4);
+                if (chunk16 == 0 && k < keys) sc[key0 + k] = s_ * 0.125f;
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < kCbKeys / 16; ++it) {
+                const int k = it * 16 + slot;
+                const float w = (k < keys) ? round_f16(sc[key0 + k] * inv) : 0.f;
+                const uint4 u = *reinterpret_cast<const uint4*>(base + k * 128 + chunk16 * 16);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h2[j]);
+                    acc[2 * j] = fmaf(w, f.x, acc[2 * j]);
+                    acc[2 * j + 1] = fmaf(w, f.y, acc[2 * j + 1]);
+                }
+            }
+        }
+        __syncthreads();  // stage consumed by everyone (and, after the last K chunk, all scores are in smem)
+        if (tid == 0 && c + kCbStages < total) issue(c + kCbStages);
+        if (c == nck - 1) {
+            // softmax over the T scores (V chunks are already streaming into the ring)
+            float mx = -INFINITY;
+            for (int t = tid; t < T; t += kCrossThreads) mx = fmaxf(mx, sc[t]);
+            mx = warp_max(mx);
+            if (lane == 0) red[warp] = mx;
+            __syncthreads();
+            mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+            float sum = 0.f;
+            for (int t = tid; t < T; t += kCrossThreads) {
+                const float e = __expf(sc[t] - mx);
+                sc[t] = e;
+                sum += e;
+            }
+            sum = warp_sum(sum);
+            if (lane == 0) red[4 + warp] = sum;
+            __syncthreads();
+            inv = 1.0f / (red[4] + red[5] + red[6] + red[7]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) osum[warp * 64 + lane * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    if (tid < 64) out[(long long)b * n + h * 64 + tid] = __float2half_rn(osum[tid] + osum[64 + tid] + osum[128 + tid] + osum[192 + tid]);
+}
+
 int launch_attn_dec_cross(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T,
                           cudaStream_t s) {
     if (T > kCrossMaxT) return set_error("attn_dec_cross: T %d > %d", T, kCrossMaxT);
     dim3 grid(H, B);
-    attn_dec_cross_kernel<<<grid, kCrossThreads, 0, s>>>(q, kv, out, done, H, T);
+    static const bool use_bulk = getenv("WJB_CROSS_LSU") == nullptr;
+    if (use_bulk) {
+        static bool attr = false;
+        if (!attr) {
+            cudaError_t e = cudaFuncSetAttribute(attn_dec_cross_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCbSmem);
+            if (e != cudaSuccess) return set_error("cross attr: %s", cudaGetErrorString(e));
+            attr = true;
+        }
+        cudaError_t e = launch_k(attn_dec_cross_bulk_kernel, grid, dim3(kCrossThreads), (size_t)kCbSmem, s, q, kv, out, done, H, T);
+        if (e != cudaSuccess) return set_error("attn_dec_cross_bulk launch: %s", cudaGetErrorString(e));
+        return 0;
+    }
+    launch_k(attn_dec_cross_kernel, grid, dim3(kCrossThreads), 0, s, q, kv, out, done, H, T);
     WJB_CHECK_LAUNCH("attn_dec_cross");
     return 0;
 }

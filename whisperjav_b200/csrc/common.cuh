@@ -176,6 +176,14 @@ WJB_DEVINL float ex2_approx(float x) {
     return y;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Top of every decoder-step kernel: let the next kernel of the chain start launching, then wait until the previous
+// grid has completed and flushed (no-ops when the launch carries no programmatic dependency).
+WJB_DEVINL void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ math
 WJB_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // Exact-erf GELU through the Abramowitz-Stegun 7.1.26 rational form of erf (|error| <= 1.5e-7, far below the

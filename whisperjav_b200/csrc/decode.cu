@@ -12,6 +12,7 @@ namespace wjb {
 
 __global__ void embed_kernel(const int* __restrict__ tokens, int tokens_stride, const __half* __restrict__ emb,
                              const __half* __restrict__ pos, __half* __restrict__ x, const DecodeCtl* __restrict__ ctl, int n) {
+    pdl_prologue();
     const int b = blockIdx.x;
     const int step = ctl->step;
     const int tok = tokens[(long long)b * tokens_stride + step];
@@ -26,7 +27,7 @@ __global__ void embed_kernel(const int* __restrict__ tokens, int tokens_stride, 
 
 int launch_embed(const int* tokens, int tokens_stride, const __half* emb, const __half* pos, __half* x, const DecodeCtl* ctl, int B,
                  int n, cudaStream_t s) {
-    embed_kernel<<<B, 128, 0, s>>>(tokens, tokens_stride, emb, pos, x, ctl, n);
+    launch_k(embed_kernel, dim3(B), dim3(128), 0, s, tokens, tokens_stride, emb, pos, x, ctl, n);
     WJB_CHECK_LAUNCH("embed");
     return 0;
 }
@@ -76,6 +77,7 @@ sample_kernel(const __half* __restrict__ logits, const unsigned char* __restrict
     __shared__ ArgMax sh_am[kSampleThreads / 32];
     __shared__ float sh_f[kSampleThreads / 32];
     __shared__ int st[4];  // last_was_ts, penult_was_ts, have_ts, timestamp_last
+    pdl_prologue();
     const int b = blockIdx.x, tid = threadIdx.x;
     const int step = ctl->step;
     const int cur_len = step + 1;
@@ -201,7 +203,10 @@ sample_kernel(const __half* __restrict__ logits, const unsigned char* __restrict
     }
 }
 
-__global__ void advance_kernel(DecodeCtl* ctl) { ctl->step += 1; }
+__global__ void advance_kernel(DecodeCtl* ctl) {
+    pdl_prologue();
+    ctl->step += 1;
+}
 
 int launch_sample(const __half* logits, const unsigned char* suppress_mask, int* tokens, const int* /*initial_tokens*/,
                   float* sum_logprob, float* no_speech_prob, int* out_len, unsigned char* done, DecodeCtl* ctl, const DecodeParams& p,
@@ -214,13 +219,13 @@ int launch_sample(const __half* logits, const unsigned char* suppress_mask, int*
         attr = true;
     }
     if (smem > 110 * 1024) return set_error("sample: vocab %d too large", p.n_vocab);
-    sample_kernel<<<p.B, kSampleThreads, smem, s>>>(logits, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, done, ctl, p);
+    launch_k(sample_kernel, dim3(p.B), dim3(kSampleThreads), smem, s, logits, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, done, ctl, p);
     WJB_CHECK_LAUNCH("sample");
     return 0;
 }
 
 int launch_advance(DecodeCtl* ctl, cudaStream_t s) {
-    advance_kernel<<<1, 1, 0, s>>>(ctl);
+    launch_k(advance_kernel, dim3(1), dim3(1), 0, s, ctl);
     WJB_CHECK_LAUNCH("advance");
     return 0;
 }

@@ -8,6 +8,7 @@ namespace wjb {
 template <int kVecPerLane>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
                                                         const __half* __restrict__ beta, __half* __restrict__ out, int rows, int n) {
+    pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -76,11 +77,11 @@ int launch_layernorm(const __half* x, const __half* gamma, const __half* beta, _
     const int grid = (rows + warps_per_block - 1) / warps_per_block;
     const int nvec = n / 8;
     if (nvec <= 64)
-        layernorm_kernel<2><<<grid, 256, 0, s>>>(x, gamma, beta, out, rows, n);
+        launch_k(layernorm_kernel<2>, dim3(grid), dim3(256), 0, s, x, gamma, beta, out, rows, n);
     else if (nvec <= 160)
-        layernorm_kernel<5><<<grid, 256, 0, s>>>(x, gamma, beta, out, rows, n);
+        launch_k(layernorm_kernel<5>, dim3(grid), dim3(256), 0, s, x, gamma, beta, out, rows, n);
     else
-        layernorm_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, out, rows, n);
+        launch_k(layernorm_kernel<8>, dim3(grid), dim3(256), 0, s, x, gamma, beta, out, rows, n);
     WJB_CHECK_LAUNCH("layernorm");
     return 0;
 }

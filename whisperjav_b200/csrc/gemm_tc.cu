@@ -63,6 +63,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
     uint8_t* stage_base = smem + Cfg::kStages * Cfg::kStageBytes + 256;  // epilogue transpose staging, 8 warps x 32 rows x 80 B
 
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: the next kernel may start launching
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int m_tiles_per_batch = (p.rows_per_batch + kBlockM - 1) / kBlockM;
@@ -91,6 +92,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: inputs of the previous kernel are complete and visible
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -316,8 +318,8 @@ static int launch_bn(const GemmArgs& a, const CUtensorMap& tmA, const GemmDev& d
     uint32_t boxB[2] = {(uint32_t)kBlockK, (uint32_t)BN};
     if (int e = encode_map(&tmB, a.W, 2, dimsB, strB, boxB)) return e;
     int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-    gemm_tc_kernel<BN><<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(tmA, tmB, d);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(kGemmThreads), (size_t)GemmCfg<BN>::kSmemBytes, stream, tmA, tmB, d);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("gemm_tc launch: %s", cudaGetErrorString(e));
     return 0;
 }

@@ -18,6 +18,28 @@ tensor_map_encode_fn get_tensor_map_encoder();
         if (e__ != cudaSuccess) return ::wjb::set_error("%s: %s", name, cudaGetErrorString(e__)); \
     } while (0)
 
+// ---- launches: optional programmatic-dependent-launch attribute (set around the decoder step) -------------
+bool pdl_enabled();
+void set_pdl(bool on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    int n = 0;
+    if (pdl_enabled()) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        n = 1;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- GEMM (gemm_tc.cu) ---------------------------------------------------------------------
 enum { GEMM_GELU = 1, GEMM_HEADSPLIT = 2 };
 struct GemmArgs {
