@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
             for (int it = 0; it < kCbKeys / 16; ++it) {
                 const int k = it * 16 + slot;
                 const float w = (k < keys) ? round_f16(sc[key0 + k] * inv) : 0.f;
-                const uint4 u = *reinterpret_cast<const uint4*>(base + k * 128 + chunk16 * 16);
+                const uint4 u = (k < keys) ? *reinterpret_cast<const uint4*>(base + k * 128 + chunk16 * 16) : make_uint4(0, 0, 0, 0);
                 const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
