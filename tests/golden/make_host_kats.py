@@ -108,3 +108,33 @@ for thr in (None, -1.0, -1.55):
 out["segment_filter"] = cases
 (HERE / "reference_host_kats.json").write_text(json.dumps(out, ensure_ascii=False))
 print({k: len(v) for k, v in out.items()})
+
+# ---- TEN frame-flag pipeline (ten.py:280-515), appended fixture
+from whisperjav.modules.speech_segmentation.backends.ten import TenSpeechSegmenter  # noqa: E402
+
+rng2 = np.random.default_rng(777)
+cases = []
+for k in range(12):
+    n = int(rng2.integers(20, 3000))
+    flags = np.zeros(n, dtype=int)
+    probs = np.clip(rng2.normal(0.1, 0.05, n), 0, 1)
+    for _ in range(int(rng2.integers(0, 8))):
+        a = int(rng2.integers(0, n))
+        b = min(n, a + int(rng2.integers(2, 1200)))
+        flags[a:b] = 1
+        probs[a:b] = np.clip(0.7 + 0.25 * np.sin(np.arange(b - a) / rng2.uniform(3, 40)) + rng2.normal(0, 0.03, b - a), 0, 1)
+    kw = dict(min_speech_duration_ms=int(rng2.choice([81, 200])), min_silence_duration_ms=int(rng2.choice([0, 100, 300])),
+              max_speech_duration_s=float(rng2.choice([3.0, 10.0])), start_pad_ms=int(rng2.choice([0, 50])), end_pad_ms=int(rng2.choice([0, 150])))
+    seg = TenSpeechSegmenter(**kw)
+    probs4 = [round(float(x), 4) for x in probs]
+    dur = n * 256 / 16000 - float(rng2.uniform(0, 0.01))
+    raw = seg._flags_to_segments(flags.tolist(), probs4, 16000, dur)
+    merged = seg._merge_by_silence(raw)
+    padded = seg._apply_padding(merged, dur)
+    final = seg._split_long_segments(padded)
+    cases.append({"flags": flags.tolist(), "probs": probs4, "duration": dur, **kw,
+                  "raw": [(r["start"], r["end"], len(r["probs"])) for r in raw],
+                  "final": [(s.start_sec, s.end_sec, s.confidence, s.metadata["raw_start"], s.metadata["raw_end"]) for s in final]})
+out["ten_pipeline"] = cases
+(HERE / "reference_host_kats.json").write_text(json.dumps(out, ensure_ascii=False))
+print({k: len(v) for k, v in out.items()})

@@ -44,6 +44,10 @@ def test_segmenter_surface_and_postprocess():
     assert seg.start_sample == max(0, int((100 * 512 - 480) ) - 11200 + 0) or seg.start_sample >= 0
     assert r.segments[1].start_sample >= r.segments[0].end_sample
     assert r.to_legacy_format()[0][0]["start"] == seg.start_sample
+    t = B200SpeechSegmenter(threshold=0.5, style="ten", min_silence_duration_ms=100, chunk_threshold_s=1.0)
+    rt = t._postprocess(probs, 480000, 30.0, {}, 0.0)
+    assert rt.num_segments == 2 and abs(rt.segments[0].start_sec - (100 * 0.032 - 0.05)) < 1e-9
+    assert abs(rt.segments[0].end_sec - (200 * 0.032 + 0.15)) < 1e-9 and "raw_start" in rt.segments[0].metadata
     empty = s._postprocess(np.zeros(100, np.float32), 51200, 3.2, {}, 0.0)
     assert empty.segments == [] and empty.groups == []
     s.cleanup()

@@ -71,3 +71,16 @@ def test_legacy_format():
     r = H.SegmentationResult([s], [[s]], "b200", 3.0, {})
     assert r.to_legacy_format() == [[{"start": 16000, "end": 32000, "start_sec": 1.0, "end_sec": 2.0, "metadata": {"k": 1}}]]
     assert r.num_segments == 1 and r.num_groups == 1 and abs(r.speech_coverage_ratio - 1 / 3) < 1e-12
+
+
+def test_ten_style_pipeline_matches_reference():
+    for c in KATS["ten_pipeline"]:
+        raw = H.flags_to_regions(c["flags"], c["probs"], 256 / 16000, c["duration"], c["min_speech_duration_ms"], c["max_speech_duration_s"])
+        assert [(r["start"], r["end"], len(r["probs"])) for r in raw] == [tuple(x) for x in c["raw"]]
+        final = H.ten_style_segments(c["flags"], c["probs"], c["duration"], min_speech_duration_ms=c["min_speech_duration_ms"],
+                                     min_silence_duration_ms=c["min_silence_duration_ms"], max_speech_duration_s=c["max_speech_duration_s"],
+                                     start_pad_ms=c["start_pad_ms"], end_pad_ms=c["end_pad_ms"])
+        got = [(s.start_sec, s.end_sec, s.confidence, s.metadata["raw_start"], s.metadata["raw_end"]) for s in final]
+        assert len(got) == len(c["final"])
+        for g, r in zip(got, c["final"]):
+            assert g[0] == r[0] and g[1] == r[1] and abs(g[2] - r[2]) < 1e-9 and g[3] == r[3] and g[4] == r[4]

@@ -235,3 +235,138 @@ class LogprobGate:
             return True
         bare = "".join(ch for ch in core if ch not in cls.IGNORED)
         return bool(bare) and len(bare) <= 6 and all(ch in cls.VOCAL_CHARS for ch in bare)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# TEN-style pipeline: per-hop speech flags -> regions -> merge -> pad -> split -> SpeechSegment
+# (speech_segmentation/backends/ten.py:280-515: _flags_to_segments, _merge_by_silence, _apply_padding,
+#  _split_long_segments, _even_split, _make_subsegment, _to_speech_segments)
+# ---------------------------------------------------------------------------------------------------------
+def flags_to_regions(flags: Sequence[int], probs: Sequence[float], frame_s: float, audio_duration: float,
+                     min_speech_duration_ms: float = 81, max_speech_duration_s: float = 10.0) -> List[Dict[str, Any]]:
+    """Runs of flag == 1 become regions {'start','end','probs'}; a run is cut (and restarted on the same frame) once it
+    has lasted ``max_speech_duration_s``; regions shorter than ``min_speech_duration_ms`` are dropped."""
+    out: List[Dict[str, Any]] = []
+    start = None
+    heard: List[float] = []
+
+    def emit(end: float):
+        if (end - start) * 1000 >= min_speech_duration_ms:
+            out.append({"start": start, "end": end, "probs": list(heard)})
+
+    for i, flag in enumerate(flags):
+        t = i * frame_s
+        if flag == 1:
+            if start is None:
+                start, heard = t, [probs[i]]
+            else:
+                heard.append(probs[i])
+                if max_speech_duration_s > 0 and t - start >= max_speech_duration_s:
+                    emit(t)
+                    start, heard = t, [probs[i]]
+        elif start is not None:
+            emit(t)
+            start, heard = None, []
+    if start is not None:
+        emit(min(len(flags) * frame_s, audio_duration))
+    return out
+
+
+def merge_close_regions(regions: Sequence[Dict[str, Any]], min_silence_duration_ms: float = 100) -> List[Dict[str, Any]]:
+    """Fuse neighbours whose gap is <= ``min_silence_duration_ms`` (probabilities are concatenated)."""
+    if not regions or min_silence_duration_ms <= 0:
+        return list(regions)
+    gap_s = min_silence_duration_ms / 1000.0
+    out: List[Dict[str, Any]] = []
+    for r in regions:
+        if out and r["start"] - out[-1]["end"] <= gap_s:
+            out[-1]["end"] = r["end"]
+            out[-1]["probs"].extend(r["probs"])
+        else:
+            out.append({"start": r["start"], "end": r["end"], "probs": list(r["probs"])})
+    return out
+
+
+def pad_regions(regions: Sequence[Dict[str, Any]], audio_duration: float, start_pad_ms: float = 50,
+                end_pad_ms: float = 150) -> List[Dict[str, Any]]:
+    """Start earlier by ``start_pad_ms``, end later by ``end_pad_ms``; a start never precedes the previous padded end."""
+    out: List[Dict[str, Any]] = []
+    for i, r in enumerate(regions):
+        a = max(0.0, r["start"] - start_pad_ms / 1000.0)
+        b = min(audio_duration, r["end"] + end_pad_ms / 1000.0)
+        if i > 0 and out and a < out[-1]["end"]:
+            a = out[-1]["end"]
+        if b > a:
+            out.append({"start": a, "end": b, "probs": r["probs"], "raw_start": r["start"], "raw_end": r["end"]})
+    return out
+
+
+def _sub_region(parent: Dict[str, Any], a: float, b: float, frame_s: float) -> Dict[str, Any]:
+    i0 = max(0, int((a - parent["start"]) / frame_s)) if frame_s > 0 else 0
+    i1 = min(len(parent["probs"]), int((b - parent["start"]) / frame_s)) if frame_s > 0 else 0
+    return {"start": a, "end": b, "probs": parent["probs"][i0:i1] if i0 < i1 else [],
+            "raw_start": parent.get("raw_start", a), "raw_end": parent.get("raw_end", b)}
+
+
+def _even_parts(r: Dict[str, Any], max_dur: float) -> List[Dict[str, Any]]:
+    import math
+    dur = r["end"] - r["start"]
+    n = max(1, int(math.ceil(dur / max_dur)))
+    part = dur / n
+    frame_s = dur / len(r["probs"]) if len(r["probs"]) > 0 else 0.016
+    return [_sub_region(r, r["start"] + i * part, min(r["start"] + i * part + part, r["end"]), frame_s) for i in range(n)]
+
+
+def split_long_regions(regions: Sequence[Dict[str, Any]], max_speech_duration_s: float = 10.0) -> List[SpeechSegment]:
+    """Regions longer than ``max_speech_duration_s`` are cut at local minima of the box-smoothed probability curve
+    (a cut only once 80 % of the limit has elapsed since the last one), else evenly."""
+    import numpy as np
+    final: List[Dict[str, Any]] = []
+    for r in regions:
+        dur = r["end"] - r["start"]
+        if max_speech_duration_s <= 0 or dur <= max_speech_duration_s:
+            final.append(r)
+            continue
+        p = r["probs"]
+        if len(p) < 2:
+            final.extend(_even_parts(r, max_speech_duration_s))
+            continue
+        arr = np.array(p, dtype=np.float32)
+        win = max(3, len(arr) // 20)
+        smooth = np.convolve(arr, np.ones(win) / win, mode="same")
+        minima = [j for j in range(1, len(smooth) - 1) if smooth[j] <= smooth[j - 1] and smooth[j] <= smooth[j + 1]]
+        frame_s = dur / len(p)
+        cuts, last = [], r["start"]
+        for j in minima:
+            t = r["start"] + j * frame_s
+            if t - last > max_speech_duration_s * 0.8:
+                cuts.append(t)
+                last = t
+        if not minima or not cuts:
+            final.extend(_even_parts(r, max_speech_duration_s))
+            continue
+        prev = r["start"]
+        for t in cuts:
+            if t - prev > 0.05:
+                final.append(_sub_region(r, prev, t, frame_s))
+                prev = t
+        if r["end"] - prev > 0.05:
+            final.append(_sub_region(r, prev, r["end"], frame_s))
+    out: List[SpeechSegment] = []
+    for r in final:
+        p = r.get("probs", [])
+        out.append(SpeechSegment(start_sec=r["start"], end_sec=r["end"], start_sample=int(r["start"] * 16000),
+                                 end_sample=int(r["end"] * 16000), confidence=(sum(p) / len(p)) if p else 1.0,
+                                 metadata={"raw_start": r.get("raw_start", r["start"]), "raw_end": r.get("raw_end", r["end"])}))
+    return out
+
+
+def ten_style_segments(flags: Sequence[int], probs: Sequence[float], audio_duration: float, *, hop_size: int = 256,
+                       sample_rate: int = 16000, min_speech_duration_ms: float = 81, min_silence_duration_ms: float = 100,
+                       max_speech_duration_s: float = 10.0, start_pad_ms: float = 50, end_pad_ms: float = 150) -> List[SpeechSegment]:
+    """detect -> merge -> pad -> split, exactly the order of TenSpeechSegmenter.segment (ten.py:241-251)."""
+    frame_s = hop_size / sample_rate
+    r = flags_to_regions(flags, probs, frame_s, audio_duration, min_speech_duration_ms, max_speech_duration_s)
+    r = merge_close_regions(r, min_silence_duration_ms)
+    r = pad_regions(r, audio_duration, start_pad_ms, end_pad_ms)
+    return split_long_regions(r, max_speech_duration_s)

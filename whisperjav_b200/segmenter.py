@@ -28,7 +28,8 @@ class B200SpeechSegmenter:
     def __init__(self, threshold: float = 0.5, min_speech_duration_ms: int = 150, min_silence_duration_ms: int = 300,
                  speech_pad_ms: int = 30, chunk_threshold_s: Optional[float] = None, max_group_duration_s: Optional[float] = None,
                  max_speech_duration_s: Optional[float] = None, start_pad_samples: int = 11200, end_pad_samples: int = 20800,
-                 device: str = "cuda", vad_state_dict: Optional[dict] = None, **kwargs: Any):
+                 device: str = "cuda", vad_state_dict: Optional[dict] = None, style: str = "silero",
+                 start_pad_ms: int = 50, end_pad_ms: int = 150, **kwargs: Any):
         self.threshold = float(threshold)
         self.min_speech_duration_ms = int(min_speech_duration_ms)
         self.min_silence_duration_ms = int(min_silence_duration_ms)
@@ -40,6 +41,10 @@ class B200SpeechSegmenter:
         self.max_speech_duration_s = float(max_speech_duration_s) if max_speech_duration_s not in (None, float("inf")) else 0.0
         self.start_pad_samples = int(start_pad_samples)
         self.end_pad_samples = int(end_pad_samples)
+        if style not in ("silero", "ten"):
+            raise ValueError("style must be 'silero' (hysteresis + sample padding) or 'ten' (flag runs + merge/pad/split)")
+        self.style = style
+        self.start_pad_ms, self.end_pad_ms = int(start_pad_ms), int(end_pad_ms)
         self._device = device
         self._sd = vad_state_dict
         self._model = None
@@ -106,6 +111,16 @@ class B200SpeechSegmenter:
         return out
 
     def _postprocess(self, probs: np.ndarray, n_audio: int, duration: float, kw: Dict[str, Any], elapsed: float):
+        if self.style == "ten":  # backends/ten.py pipeline on 512-sample hops: flags = prob >= threshold
+            thr = kw.get("threshold", self.threshold)
+            flags = [1 if float(p) >= thr else 0 for p in probs]
+            segs = H.ten_style_segments(flags, [float(p) for p in probs], n_audio / VAD_SR, hop_size=WINDOW,
+                                        min_speech_duration_ms=kw.get("min_speech_duration_ms", self.min_speech_duration_ms),
+                                        min_silence_duration_ms=kw.get("min_silence_duration_ms", self.min_silence_duration_ms),
+                                        max_speech_duration_s=self.max_speech_duration_s or 10.0,
+                                        start_pad_ms=self.start_pad_ms, end_pad_ms=self.end_pad_ms)
+            groups = H.group_by_gap(segs, self.max_group_duration_s, self.chunk_threshold_s)
+            return H.SegmentationResult(segs, groups, self.name, duration, self._get_parameters(), elapsed)
         regions = H.probs_to_regions(
             probs, n_audio / VAD_SR, frame_ms=1000.0 * WINDOW / VAD_SR, threshold=kw.get("threshold", self.threshold),
             min_speech_duration_ms=kw.get("min_speech_duration_ms", self.min_speech_duration_ms),
