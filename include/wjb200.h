@@ -94,6 +94,8 @@ typedef struct wjb_decode_opts {
     int32_t max_initial_timestamp_index;  /* -1 = none */
     int32_t tokens_stride;                /* ints per row of `tokens` (>= n_initial + sample_len + 1) */
     int32_t check_every;                  /* host polls the done counter every this many steps (0 = 8) */
+    float temperature;                    /* 0 = greedy argmax; > 0 = Categorical(logits / T) by Gumbel-max, counter-based RNG */
+    uint32_t seed;                        /* RNG stream for temperature > 0 (row, step and token id are mixed in) */
 } wjb_decode_opts;
 
 size_t wjb_decode_workspace_bytes(const wjb_model* m, int batch);

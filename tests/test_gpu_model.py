@@ -128,3 +128,33 @@ def test_transcribe_matches_oracle(tiny, clips, diag_dir):
         else:
             assert [round(s_["start"], 2) for s_ in g["segments"]][:2] == [round(s_["start"], 2) for s_ in ref["segments"]][:2]
     (diag_dir / "transcribe_tiny.json").write_text(json.dumps(report))
+
+
+def test_temperature_fallback_and_sampling(tiny, clips):
+    """T > 0 draws from Categorical(logits / T): different seeds give different valid sequences, T -> 0+ reproduces
+    greedy, and the fallback ladder re-decodes exactly the windows that fail the thresholds."""
+    dims, w, m = tiny
+    mel_tm = _gpu_mel(m, clips[:3])
+    xa = m.encode(mel_tm)
+    greedy = m.decode_features(xa, language="ja", max_initial_timestamp=0.0, temperature=0.0)
+    cold = m.decode_features(xa, language="ja", max_initial_timestamp=0.0, temperature=1e-4, seed=1)
+    assert [r.tokens[:6] for r in cold] == [r.tokens[:6] for r in greedy]  # exact ties (fp16 logits) may break differently later on
+    a = m.decode_features(xa, language="ja", max_initial_timestamp=0.0, temperature=1.0, seed=1)
+    b = m.decode_features(xa, language="ja", max_initial_timestamp=0.0, temperature=1.0, seed=2)
+    a2 = m.decode_features(xa, language="ja", max_initial_timestamp=0.0, temperature=1.0, seed=1)
+    assert [r.tokens for r in a] == [r.tokens for r in a2]           # counter-based RNG: reproducible
+    assert [r.tokens for r in a] != [r.tokens for r in b]            # and seed-dependent
+    tok = M.Tokens(dims.n_vocab, "ja")
+    banned = set(tok.suppress_list("-1")) | {tok.no_timestamps}
+    for r in a + b:
+        assert not (set(r.tokens) & banned) and r.tokens[0] >= tok.timestamp_begin and r.avg_logprob < 0
+    # ladder: an impossible logprob threshold sends every window down the ladder; the last temperature's result is kept
+    p0 = m.stats["device_passes"]
+    out = m.transcribe_batch(clips[:2], language="ja", temperature=(0.0, 0.5, 1.0), logprob_threshold=0.0, no_speech_threshold=None,
+                             compression_ratio_threshold=None, condition_on_previous_text=False, max_initial_timestamp=0.0, best_of=2)
+    assert all(s_["temperature"] == 1.0 for o in out for s_ in o["segments"])
+    assert m.stats["device_passes"] - p0 >= 1 + 2 + 2                # T=0 once, then best_of=2 at each T > 0
+    p0 = m.stats["device_passes"]
+    out = m.transcribe_batch(clips[:2], language="ja", temperature=(0.0, 0.5), logprob_threshold=-50.0, no_speech_threshold=None,
+                             compression_ratio_threshold=None, condition_on_previous_text=False, max_initial_timestamp=0.0)
+    assert all(s_["temperature"] == 0.0 for o in out for s_ in o["segments"])

@@ -24,7 +24,7 @@ class DecodeOpts(C.Structure):
     _fields_ = [(k, C.c_int32) for k in (
         "n_initial", "sot_index", "sample_len", "eot", "no_speech", "no_timestamps", "timestamp_begin",
         "suppress_blank", "blank_token", "apply_timestamp_rules", "max_initial_timestamp_index",
-        "tokens_stride", "check_every")]
+        "tokens_stride", "check_every")] + [("temperature", C.c_float), ("seed", C.c_uint32)]
 
 
 _SIGS = {

@@ -670,6 +670,9 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
     cudaEventRecord(m->ev, (cudaStream_t)stream);
     cudaStreamWaitEvent(s, m->ev, 0);
     const wjb_decode_opts& o = *opts;
+    wjb_decode_opts okey = o;  // graph identity: everything except the run-time sampling knobs
+    okey.temperature = 0.f;
+    okey.seed = 0;
     if (o.n_initial < 1 || o.sample_len < 1) return set_error("decode: bad n_initial/sample_len");
     const int total_steps = o.n_initial - 1 + o.sample_len;
     if (total_steps > d.n_text_ctx) return set_error("decode: n_initial + sample_len exceeds n_text_ctx");
@@ -684,6 +687,8 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
     h_ctl.sot_index = o.sot_index;
     h_ctl.max_steps = o.sample_len;
     h_ctl.n_done = 0;
+    h_ctl.temperature = o.temperature;
+    h_ctl.seed = o.seed;
     cudaError_t ce;
     if ((ce = cudaMemcpyAsync(w.ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, s)) != cudaSuccess)
         return set_error("decode ctl copy: %s", cudaGetErrorString(ce));
@@ -728,7 +733,7 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
     if (use_graph) {
         const bool hit = m->graph && m->g_kv == cross_kv && m->g_ws == workspace && m->g_B == batch && m->g_mask == suppress_mask &&
                          m->g_tokens == tokens && m->g_slp == sum_logprob && m->g_nsp == no_speech_prob && m->g_len == out_len &&
-                         m->g_split == split && memcmp(&m->g_opts, &o, sizeof(o)) == 0;
+                         m->g_split == split && memcmp(&m->g_opts, &okey, sizeof(okey)) == 0;
         if (!hit) {
             if (m->graph) {
                 cudaGraphExecDestroy(m->graph);
@@ -759,7 +764,7 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
             m->g_slp = sum_logprob;
             m->g_nsp = no_speech_prob;
             m->g_len = out_len;
-            m->g_opts = o;
+            m->g_opts = okey;
             m->g_split = split;
         }
     }

@@ -174,22 +174,36 @@ sample_kernel(const __half* __restrict__ logits, const unsigned char* __restrict
     }
     s_text = block_sum(s_text, sh_f);
     s_ts = block_sum(s_ts, sh_f);
+    bool ts_wins = false;
+    if (p.apply_timestamp_rules && s_ts > 0.f) {
+        // logsumexp(timestamp logprobs) > max text logprob  <=>  log(s_ts) + mx > max text logit
+        ts_wins = (logf(s_ts) + mx) > at.v;
+    }
+    ArgMax pick = ts_wins ? as : amax(at, as);
+    const float temperature = ctl->temperature;
+    if (temperature > 0.f) {
+        // GreedyDecoder.update at T > 0: Categorical(logits / T) over the filtered logits, drawn by Gumbel-max with a
+        // counter-based generator keyed on (seed, row, step, token id); logprobs below stay those of the unscaled logits
+        const float inv_t = 1.0f / temperature;
+        const unsigned seed = ctl->seed;
+        ArgMax g{-INFINITY, 0x7fffffff};
+        for (int v = tid; v < V; v += kSampleThreads) {
+            const float l = __half2float(srow[v]);
+            if (l == -INFINITY || (ts_wins && v < split)) continue;
+            unsigned hsh = seed ^ (0x9E3779B9u * (unsigned)(b + 1)) ^ (0x85EBCA6Bu * (unsigned)(step + 1)) ^ (0xC2B2AE35u * (unsigned)(v + 1));
+            hsh ^= hsh >> 16;
+            hsh *= 0x7feb352du;
+            hsh ^= hsh >> 15;
+            hsh *= 0x846ca68bu;
+            hsh ^= hsh >> 16;
+            const float u = (float)(hsh >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f);  // (0, 1)
+            g = amax(g, ArgMax{l * inv_t - logf(-logf(u)), v});
+        }
+        pick = block_argmax(g, sh_am);
+    }
     if (tid == 0) {
-        int tok;
-        float lse;
-        bool ts_wins = false;
-        if (p.apply_timestamp_rules && s_ts > 0.f) {
-            // logsumexp(timestamp logprobs) > max text logprob  <=>  log(s_ts) + mx > max text logit
-            ts_wins = (logf(s_ts) + mx) > at.v;
-        }
-        if (ts_wins) {
-            tok = as.i;
-            lse = mx + logf(s_ts);
-        } else {
-            const ArgMax best = amax(at, as);
-            tok = best.i;
-            lse = mx + logf(s_text + s_ts);
-        }
+        const int tok = pick.i;
+        const float lse = ts_wins ? mx + logf(s_ts) : mx + logf(s_text + s_ts);
         const float lp = __half2float(srow[tok]) - lse;
         sum_logprob[b] += lp;
         if (cur_len < p.tokens_stride) trow[cur_len] = tok;

@@ -107,6 +107,8 @@ struct DecodeCtl {            // device-resident control block, one per decode r
     int sot_index;
     int max_steps;            // sample_len
     int n_done;
+    float temperature;        // 0 = argmax; read by sample_kernel at run time so the step graph does not depend on it
+    unsigned seed;
 };
 struct DecodeParams {
     int B, n_vocab, logits_stride;

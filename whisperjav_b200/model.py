@@ -152,6 +152,7 @@ class WhisperB200:
         self._bufs: Dict[str, torch.Tensor] = {}
         self._pinned: Dict[str, torch.Tensor] = {}
         self.stats = {"windows": 0, "decode_steps": 0, "device_passes": 0}
+        self._sample_calls = 0
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -211,8 +212,9 @@ class WhisperB200:
     def decode_features(self, xa: torch.Tensor, *, language="ja", task="transcribe", without_timestamps=False,
                         suppress_tokens="-1", suppress_blank=True, max_initial_timestamp: Optional[float] = 1.0,
                         sample_len: Optional[int] = None, prompt: Optional[Sequence[int]] = None,
-                        prefix: Optional[Sequence[int]] = None, temperature: float = 0.0) -> List[DecodingResult]:
-        """Greedy decode of B windows (upstream DecodingTask.run, T == 0) in one device-resident loop."""
+                        prefix: Optional[Sequence[int]] = None, temperature: float = 0.0, seed: int = 0) -> List[DecodingResult]:
+        """Decode B windows (upstream DecodingTask.run with GreedyDecoder: argmax at T == 0, Categorical(logits / T)
+        otherwise) in one device-resident loop."""
         d = self.dims
         B = xa.shape[0]
         tok = Tokens(d.n_vocab, language, task)
@@ -238,6 +240,7 @@ class WhisperB200:
             mi = round(max_initial_timestamp / (30.0 / d.n_audio_ctx))
         opts.max_initial_timestamp_index = mi
         opts.tokens_stride, opts.check_every = stride, 8
+        opts.temperature, opts.seed = float(temperature), int(seed) & 0xFFFFFFFF
 
         key = ("mask", hash(str(suppress_tokens)), language, task)
         mask = self._bufs.get(key)
@@ -302,9 +305,10 @@ class WhisperB200:
         language = decode_options.pop("language", None) or "ja"
         task = decode_options.pop("task", "transcribe")
         decode_options.pop("fp16", None)
-        if decode_options.pop("beam_size", None) or (decode_options.pop("best_of", None) or 1) > 1:
+        best_of = decode_options.pop("best_of", None) or 1
+        if decode_options.pop("beam_size", None):
             import logging
-            logging.getLogger("whisperjav").warning("b200 backend: beam search / best_of not built yet; decoding greedily")
+            logging.getLogger("whisperjav").warning("b200 backend: beam search not built yet; T == 0 passes decode greedily")
         decode_options.pop("patience", None)
         decode_options.pop("length_penalty", None)
         temps = [temperature] if isinstance(temperature, (int, float)) else list(temperature)
@@ -344,7 +348,8 @@ class WhisperB200:
                 xa = self.encode(win)
                 _mark("encode")
                 prompts = [state[i]["all_tokens"][state[i]["reset"]:] for i in chunk]
-                results = self._decode_with_prompts(xa, prompts, temps[0], language, task, decode_options)
+                results = self._decode_with_fallback(xa, prompts, temps, best_of, language, task, decode_options,
+                                                     compression_ratio_threshold, logprob_threshold, no_speech_threshold)
                 _mark("decode")
                 for j, i in enumerate(chunk):
                     self._advance(state[i], results[j], tok, sizes[j], no_speech_threshold, logprob_threshold,
@@ -399,7 +404,43 @@ class WhisperB200:
             win[j, 1: 1 + z] = mel[i, 1 + s: 1 + s + z]
         return win
 
-    def _decode_with_prompts(self, xa, prompts, temperature, language, task, decode_options):
+    def _decode_with_fallback(self, xa, prompts, temps, best_of, language, task, decode_options, cr_thr, lp_thr, ns_thr):
+        """upstream transcribe.py::decode_with_fallback, batched: every window is decoded at temps[0]; windows whose result
+        looks degenerate (compression ratio too high, or average log-probability too low unless the window is judged
+        silent) are re-decoded as a smaller batch at the next temperature; at T > 0 ``best_of`` samples are drawn per
+        window and ranked by sum_logprob / length (MaximumLikelihoodRanker with length_penalty=None)."""
+        n = len(prompts)
+        final: List[Optional[DecodingResult]] = [None] * n
+        todo = list(range(n))
+        for ti, t in enumerate(temps):
+            if not todo:
+                break
+            sub_xa = xa if len(todo) == n else xa[torch.tensor(todo, device=self.device)].contiguous()
+            sub_prompts = [prompts[i] for i in todo]
+            group = best_of if (t > 0 and best_of > 1) else 1
+            cands = []
+            for g in range(group):
+                self._sample_calls += 1
+                cands.append(self._decode_with_prompts(sub_xa, sub_prompts, t, language, task, decode_options,
+                                                       seed=0x5EED0000 + 7919 * self._sample_calls))
+            still = []
+            for k, i in enumerate(todo):
+                opts_k = [c[k] for c in cands]
+                best = max(opts_k, key=lambda r: r.sum_logprob / max(len(r.tokens), 1)) if group > 1 else opts_k[0]
+                final[i] = best
+                needs = False
+                if cr_thr is not None and best.compression_ratio > cr_thr:
+                    needs = True
+                if lp_thr is not None and best.avg_logprob < lp_thr:
+                    needs = True
+                if ns_thr is not None and best.no_speech_prob > ns_thr and lp_thr is not None and best.avg_logprob < lp_thr:
+                    needs = False
+                if needs and ti + 1 < len(temps):
+                    still.append(i)
+            todo = still
+        return final
+
+    def _decode_with_prompts(self, xa, prompts, temperature, language, task, decode_options, seed: int = 0):
         # windows with identical prompts share one device pass (the common case: no prompt at all)
         groups: Dict[tuple, List[int]] = {}
         for j, p in enumerate(prompts):
@@ -407,7 +448,7 @@ class WhisperB200:
         results: List[Optional[DecodingResult]] = [None] * len(prompts)
         for p, idxs in groups.items():
             sub = xa if len(idxs) == len(prompts) else xa[torch.tensor(idxs, device=self.device)].contiguous()
-            res = self.decode_features(sub, language=language, task=task, prompt=list(p) or None, temperature=temperature,
+            res = self.decode_features(sub, language=language, task=task, prompt=list(p) or None, temperature=temperature, seed=seed,
                                        **{k: v for k, v in decode_options.items() if k in
                                           ("without_timestamps", "suppress_tokens", "suppress_blank", "max_initial_timestamp",
                                            "sample_len", "prefix")})
