@@ -113,6 +113,17 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
 int wjb_gemm_f16(const void* A, int64_t a_row_stride, int64_t a_batch_stride, int rows_per_batch, int n_batch, int K,
                  const void* W, int N, int ldw, const void* bias, const void* residual, void* out, int64_t out_row_stride,
                  int64_t out_batch_stride, int flags, int block_n, void* stream);
+/* the same GEMM for few rows (<= 128, one decoder step) with K sliced over `splits` CTAs per output tile (-1 = as many as fill
+ * the SMs); the slices meet in `workspace` (fp32) and the last CTA to arrive adds them in slice order, so results do not
+ * depend on timing.  workspace: wjb_gemm_splitk_workspace_bytes() bytes, zeroed once by the caller, not shared with a
+ * GEMM running concurrently. */
+size_t wjb_gemm_splitk_workspace_bytes(void);
+int wjb_gemm_f16_splitk(const void* A, int64_t a_row_stride, int rows, int K, const void* W, int N, int ldw, const void* bias,
+                        const void* residual, void* out, int64_t out_row_stride, int flags, int block_n, int splits,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* debugging aid: CTA 0 of every following GEMM launch writes a timeline (SM clock, global timer per pipeline event) into
+ * `buf` (device, (32 + 256 * 32) uint64, zeroed by the caller); NULL switches it off. */
+void wjb_debug_gemm_trace(void* buf);
 /* tuning hook for the decode-step GEMM: columns per CTA = 8*nt (nt 1|2|4), ks = K slices per column group (cluster size);
  * 0 = built-in heuristic */
 void wjb_gemm_skinny_config(int nt, int ks);

@@ -75,6 +75,41 @@ def test_gemm_epilogues(lib):
     gemm(lib, A, W, bias=bias, res=x, out=x)
     assert (x.float() - ref).abs().max().item() <= 8e-3
 
+@pytest.mark.parametrize("M,N,K,bn,splits", [(64, 1280, 1280, 64, -1), (64, 1280, 1280, 32, 3), (64, 3840, 1280, 64, 2), (33, 5120, 1280, 64, -1),
+                                             (64, 1280, 5120, 64, 7), (1, 1280, 1280, 64, -1), (128, 1280, 5120, 128, 5), (100, 384, 384, 64, 3)])
+def test_gemm_splitk_decode(lib, M, N, K, bn, splits):
+    """tcgen05 GEMM with K sliced over CTAs (decoder steps): every epilogue, repeated launches on one workspace, and
+    bit-identical results from run to run (the slices are added in a fixed order by the last CTA to arrive)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g)).half().to(DEV)
+    W = (torch.randn(N, K, generator=g) * 0.03).half().to(DEV)
+    bias = (torch.randn(N, generator=g) * 0.3).half().to(DEV)
+    res = (torch.randn(M, N, generator=g)).half().to(DEV)
+    ws_bytes = lib.wjb_gemm_splitk_workspace_bytes()
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=DEV)
+    lin = r16(A.float() @ W.float().t() + bias.float())
+    for flags, use_res in ((0, False), (1, False), (0, True)):
+        outs = []
+        for rep in range(3):
+            out = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+            rbuf = None
+            if use_res:
+                out.copy_(res)
+                rbuf = out  # in place, as the decoder uses it
+            _lib.check(lib.wjb_gemm_f16_splitk(_lib.ptr(A), K, M, K, _lib.ptr(W), N, K, _lib.ptr(bias), _lib.ptr(rbuf), _lib.ptr(out), N, flags, bn,
+                                               splits, _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "split-K gemm")
+            torch.cuda.synchronize()
+            outs.append(out)
+        ref = lin
+        if flags:
+            ref = r16(torch.nn.functional.gelu(lin))
+        if use_res:
+            ref = r16(lin + res.float())
+        err = (outs[0].float() - ref).abs().max().item()
+        assert err <= 8e-3 * max(1.0, ref.abs().max().item() / 4), (flags, use_res, err)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert int(ws[:4096].view(torch.int32).abs().sum().item()) == 0  # the counters are back at zero
+
 
 @pytest.mark.parametrize("M,N,K", [(64, 1280, 1280), (64, 3840, 1280), (64, 1280, 5120), (1, 384, 384), (7, 51866, 384), (33, 5120, 1280)])
 def test_gemm_skinny_decode(lib, M, N, K):

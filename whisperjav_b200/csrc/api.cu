@@ -467,9 +467,12 @@ struct DecWs {
     MegaLayer* mega_layers;
     unsigned* mega_bar;
     unsigned long long* mega_prof;
+    uint8_t* splitk;  // per decode branch: kSplitKCounters counters, then kSplitKBytes of fp32 partial tiles
     int logits_stride;
     size_t total;
 };
+constexpr size_t kSplitKBytes = 8u << 20;
+constexpr size_t kSplitKSlot = kSplitKCounters * sizeof(unsigned) + kSplitKBytes;
 static DecWs dec_ws(const wjb_dims& d, int B, uint8_t* base) {
     DecWs w;
     const size_t n = d.n_text_state;
@@ -493,6 +496,7 @@ static DecWs dec_ws(const wjb_dims& d, int B, uint8_t* base) {
     w.mega_layers = (MegaLayer*)take(sizeof(MegaLayer) * d.n_text_layer);
     w.mega_bar = (unsigned*)take(256);
     w.mega_prof = (unsigned long long*)take(8 * 1024);
+    w.splitk = take(kSplitKSlot * wjb_model::kMaxSplit);
     w.total = off;
     return w;
 }
@@ -503,7 +507,7 @@ size_t wjb_decode_workspace_bytes(const wjb_model* m, int batch) {
 }
 
 // One decoder step for the batch rows [b0, b0 + B) of a run over Btot rows, on stream s.
-static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, int Btot, int b0, int B, const wjb_decode_opts& o,
+static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, int Btot, int b0, int B, int branch, const wjb_decode_opts& o,
                          const uint8_t* suppress_mask, int32_t* tokens0, float* slp0, float* nsp0, int32_t* out_len0, cudaStream_t s) {
     const wjb_dims& d = m->d;
     const int n = d.n_text_state, H = d.n_text_head, T = d.n_audio_ctx;
@@ -539,6 +543,18 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
         q.out_row_stride = out_stride;
         q.flags = flags;
         q.block_n = 0;  // auto: 32-wide tiles when that still leaves SMs idle, else 64
+        // a step GEMM has 20-80 output tiles.  Slicing K over more CTAs pays only for the long-K one (fc2: 26 -> 16 us in the
+        // step graph); for K = n_state the meet-in-L2 costs more than the shorter k loop saves (scripts/gemm_graph_probe.py)
+        static const int splitk = getenv("WJB_DECODE_SPLITK") ? atoi(getenv("WJB_DECODE_SPLITK")) : 3;
+        static const int splitk_bn = getenv("WJB_DECODE_SPLITK_BN") ? atoi(getenv("WJB_DECODE_SPLITK_BN")) : 32;
+        static const int splitk_min_k = getenv("WJB_DECODE_SPLITK_MINK") ? atoi(getenv("WJB_DECODE_SPLITK_MINK")) : 4096;
+        if (splitk != 0 && N % 64 == 0 && K >= splitk_min_k) {
+            q.splits = splitk;
+            q.block_n = splitk_bn;
+            q.splitk_cnt = reinterpret_cast<unsigned*>(w.splitk + kSplitKSlot * branch);
+            q.splitk_ws = reinterpret_cast<float*>(w.splitk + kSplitKSlot * branch + kSplitKCounters * sizeof(unsigned));
+            q.splitk_ws_bytes = kSplitKBytes;
+        }
         if (skip & 2) return 0;
         static const bool use_skinny = getenv("WJB_DECODE_SKINNY") != nullptr;
         if (use_skinny && B <= 64 && K % 32 == 0)
@@ -640,7 +656,7 @@ static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B
     }
     if (split > B) split = B;
     if (split <= 1) {
-        if (int e = decode_branch(m, w, cross_kv, B, 0, B, o, suppress_mask, tokens, slp, nsp, out_len, s)) return e;
+        if (int e = decode_branch(m, w, cross_kv, B, 0, B, 0, o, suppress_mask, tokens, slp, nsp, out_len, s)) return e;
         return launch_advance(w.ctl, s);
     }
     cudaEventRecord(m->ev_fork, s);
@@ -649,7 +665,7 @@ static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B
         const int b0 = (int)((long long)B * i / split), b1 = (int)((long long)B * (i + 1) / split);
         cudaStream_t bs = (i == 0) ? s : m->br_stream[i];
         if (i > 0) cudaStreamWaitEvent(bs, m->ev_fork, 0);
-        if (!rc) rc = decode_branch(m, w, cross_kv, B, b0, b1 - b0, o, suppress_mask, tokens, slp, nsp, out_len, bs);
+        if (!rc) rc = decode_branch(m, w, cross_kv, B, b0, b1 - b0, i, o, suppress_mask, tokens, slp, nsp, out_len, bs);
         if (i > 0) {
             cudaEventRecord(m->ev_join[i], bs);
             cudaStreamWaitEvent(s, m->ev_join[i], 0);
@@ -721,6 +737,7 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
         cudaStreamSynchronize(s);  // tab is a stack-lifetime host buffer
     }
     cudaMemsetAsync(w.done, 0, batch, s);
+    for (int i = 0; i < wjb_model::kMaxSplit; ++i) cudaMemsetAsync(w.splitk + kSplitKSlot * i, 0, kSplitKCounters * sizeof(unsigned), s);
     cudaMemsetAsync(sum_logprob, 0, sizeof(float) * batch, s);
     cudaMemsetAsync(no_speech_prob, 0, sizeof(float) * batch, s);
     cudaMemsetAsync(out_len, 0, sizeof(int32_t) * batch, s);
@@ -852,6 +869,36 @@ int wjb_gemm_f16(const void* A, int64_t a_row_stride, int64_t a_batch_stride, in
     g.out_batch_stride = out_batch_stride;
     g.flags = flags & GEMM_GELU;
     g.block_n = block_n;
+    return launch_gemm(g, (cudaStream_t)stream);
+}
+
+size_t wjb_gemm_splitk_workspace_bytes(void) { return kSplitKSlot; }
+
+void wjb_debug_gemm_trace(void* buf) { gemm_set_trace(buf); }
+
+int wjb_gemm_f16_splitk(const void* A, int64_t a_row_stride, int rows, int K, const void* W, int N, int ldw, const void* bias,
+                        const void* residual, void* out, int64_t out_row_stride, int flags, int block_n, int splits, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    if (!workspace || workspace_bytes < kSplitKCounters * sizeof(unsigned) + (1u << 20)) return set_error("gemm split-K: workspace too small");
+    GemmArgs g;
+    g.A = (const __half*)A;
+    g.a_row_stride = a_row_stride;
+    g.rows_per_batch = rows;
+    g.n_batch = 1;
+    g.K = K;
+    g.W = (const __half*)W;
+    g.N = N;
+    g.ldw = ldw;
+    g.bias = (const __half*)bias;
+    g.residual = (const __half*)residual;
+    g.out = (__half*)out;
+    g.out_row_stride = out_row_stride;
+    g.flags = flags & GEMM_GELU;
+    g.block_n = block_n;
+    g.splits = splits;
+    g.splitk_cnt = reinterpret_cast<unsigned*>(workspace);
+    g.splitk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kSplitKCounters * sizeof(unsigned));
+    g.splitk_ws_bytes = workspace_bytes - kSplitKCounters * sizeof(unsigned);
     return launch_gemm(g, (cudaStream_t)stream);
 }
 

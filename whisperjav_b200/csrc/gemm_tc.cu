@@ -47,7 +47,22 @@ struct GemmDev {
     int rows_per_batch, n_batch, N, K;
     int flags;
     int hs_T, hs_H;  // head-split output: row (b, t) col c -> ((b*H + c/64)*T + t)*64 + c%64
+    int splits;      // split-K: work item = (tile, k slice); partial tiles meet in sk_ws, the last arriver finishes the tile
+    float* sk_ws;    // [tiles][splits][128][BN] fp32
+    unsigned* sk_cnt;  // [tiles], zero between launches
+    unsigned long long* trace;  // debugging aid: per-launch timeline of CTA 0 (null = off)
 };
+
+// timeline slot k of this launch: SM clock and global timer
+#define WJB_TRACE(k)                                                                  \
+    do {                                                                              \
+        if (trace_row) {                                                              \
+            unsigned long long gt_;                                                   \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                   \
+            trace_row[2 * (k)] = clock64();                                           \
+            trace_row[2 * (k) + 1] = gt_;                                             \
+        }                                                                             \
+    } while (0)
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -61,16 +76,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
     uint64_t* tempty_bar = bars + 2 * Cfg::kStages + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+    uint32_t* sk_flag = tmem_slot + 1;
     uint8_t* stage_base = smem + Cfg::kStages * Cfg::kStageBytes + 256;  // epilogue transpose staging, 8 warps x 32 rows x 80 B
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: the next kernel may start launching
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    __shared__ unsigned long long* trace_row_sh;
+    if (p.trace && threadIdx.x == 0) {
+        unsigned long long* r = nullptr;
+        if (blockIdx.x == 0) {
+            const unsigned long long idx = atomicAdd(p.trace, 1ull);
+            if (idx < 256) r = p.trace + 32 + idx * 32;
+            if (r) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                r[30] = smid;
+            }
+        }
+        trace_row_sh = r;
+    }
+    unsigned long long* trace_row = nullptr;
+    if (p.trace) {
+        if (threadIdx.x == 0) trace_row = trace_row_sh;
+        WJB_TRACE(0);
+    }
     const int m_tiles_per_batch = (p.rows_per_batch + kBlockM - 1) / kBlockM;
     const int tiles_m = m_tiles_per_batch * p.n_batch;
     const int tiles_n = (p.N + BN - 1) / BN;
-    const int num_tiles = tiles_m * tiles_n;
-    const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+    const int splits = p.splits > 1 ? p.splits : 1;
+    const int num_tiles = tiles_m * tiles_n * splits;  // work items: the k slices of a tile are adjacent
+    const int num_kb_total = (p.K + kBlockK - 1) / kBlockK;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -92,24 +128,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (p.trace) trace_row = trace_row_sh;  // every role's elected lane may stamp
+    if (threadIdx.x == 0) WJB_TRACE(1);
     asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: inputs of the previous kernel are complete and visible
+    if (threadIdx.x == 0) WJB_TRACE(2);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+                const int tile = item / splits, ks = item % splits;
                 const int nt = tile % tiles_n, mt = tile / tiles_n;
                 const int b = mt / m_tiles_per_batch;
                 const int row0 = (mt % m_tiles_per_batch) * kBlockM;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb0 = num_kb_total * ks / splits, kb1 = num_kb_total * (ks + 1) / splits;
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
                     uint8_t* sb = sa + Cfg::kStageBytesA;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     tma_load_3d(sa, &tmA, &full_bar[stage], kb * kBlockK, row0, b);
                     tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, nt * BN);
+                    if (kb == kb0 && item == (int)blockIdx.x) WJB_TRACE(3);
                     if (++stage == Cfg::kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -125,13 +167,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+                const int ks = item % splits;
+                const int num_kb = num_kb_total * (ks + 1) / splits - num_kb_total * ks / splits;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (kb == 0 && item == (int)blockIdx.x) WJB_TRACE(4);
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
                     const uint32_t sb = sa + Cfg::kStageBytesA;
                     const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
@@ -148,6 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 umma_commit(&tfull_bar[acc]);
+                if (item == (int)blockIdx.x) WJB_TRACE(5);
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -162,125 +208,195 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* stg = stage_base + (warp - kEpiWarp0) * (32 * kStgRowBytes);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+            const int tile = item / splits, ks = item % splits;
             const int nt = tile % tiles_n, mt = tile / tiles_n;
             const int b = mt / m_tiles_per_batch;
             const int row_base = (mt % m_tiles_per_batch) * kBlockM + q * 32;  // first of this warp's 32 rows
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
+            if (warp == kEpiWarp0 && lane == 0 && item == (int)blockIdx.x) WJB_TRACE(6);
             const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + ch * kColsPerWarp;
-#pragma unroll 1
-            for (int c = 0; c < kColsPerWarp; c += 32) {
+
+            // bias / GELU / positional / residual on one 32-column chunk of this thread's row, then the transposed store
+            auto finish_chunk = [&](float (&v)[32], int c, const uint4 (&resv)[4]) {
                 const int col0 = nt * BN + ch * kColsPerWarp + c;
-                // residual for the (row, 8-column piece) slots this lane will own after the transpose: issue the loads
-                // before the TMEM read so their latency hides behind it
-                uint4 resv[4];
+                if (p.bias) {
+                    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        uint4 bb = __ldg(bp + j4);
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&bb);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float2 f = __half22float2(h2[j]);
+                            v[j4 * 8 + 2 * j] += f.x;
+                            v[j4 * 8 + 2 * j + 1] += f.y;
+                        }
+                    }
+                }
+                if (p.flags & GEMM_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(round_f16(v[j]));
+                }
+                // ---- transpose through smem so that global accesses are 64 B contiguous per row
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    uint4 o;
+                    __half2* h2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(v[j4 * 8 + 2 * j], v[j4 * 8 + 2 * j + 1]);
+                    *reinterpret_cast<uint4*>(stg + lane * kStgRowBytes + j4 * 16) = o;
+                }
+                __syncwarp();
+                const int piece = lane & 3;
+                const int colp = col0 + piece * 8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = (lane >> 2) + 8 * i;
+                    const int grow = row_base + rr;
+                    if (grow < p.rows_per_batch && colp < p.N) {
+                        uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kStgRowBytes + piece * 16);
+                        long long off;
+                        if (p.flags & GEMM_HEADSPLIT) {
+                            off = ((long long)(b * p.hs_H + colp / 64) * p.hs_T + grow) * 64 + (colp % 64);
+                        } else {
+                            off = (long long)b * p.out_batch_stride + (long long)grow * p.out_row_stride + colp;
+                        }
+                        if (p.pos || p.residual) {
+                            __half2* h2 = reinterpret_cast<__half2*>(&val);
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float2 t = __half22float2(h2[j]);
+                                f[2 * j] = t.x;
+                                f[2 * j + 1] = t.y;
+                            }
+                            if (p.pos) {
+                                const float4* pp = reinterpret_cast<const float4*>(p.pos + (long long)grow * p.N + colp);
+                                const float4 a0 = __ldg(pp), a1 = __ldg(pp + 1);
+                                f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
+                                f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = round_f16(f[j]);
+                            }
+                            if (p.residual) {
+                                const uint4 rv = resv[i];
+                                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float2 t = __half22float2(rh[j]);
+                                    f[2 * j] += t.x;
+                                    f[2 * j + 1] += t.y;
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                        }
+                        if (colp + 8 <= p.N) {
+                            *reinterpret_cast<uint4*>(p.out + off) = val;
+                        } else {
+                            const __half* hv = reinterpret_cast<const __half*>(&val);
+                            for (int j = 0; j < 8 && colp + j < p.N; ++j) p.out[off + j] = hv[j];
+                        }
+                    }
+                }
+                __syncwarp();
+            };
+            // residual for the (row, 8-column piece) slots this lane owns after the transpose
+            auto load_residual = [&](uint4 (&resv)[4], int c) {
+                const int col0 = nt * BN + ch * kColsPerWarp + c;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) resv[i] = make_uint4(0, 0, 0, 0);
                 if (p.residual && col0 < p.N) {
-                    const int piece_ = lane & 3, colp_ = col0 + piece_ * 8;
+                    const int colp_ = col0 + (lane & 3) * 8;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int grow_ = row_base + (lane >> 2) + 8 * i;
-                        resv[i] = make_uint4(0, 0, 0, 0);
                         if (grow_ < p.rows_per_batch && colp_ + 8 <= p.N) {
                             const long long off_ = (long long)b * p.out_batch_stride + (long long)grow_ * p.out_row_stride + colp_;
                             resv[i] = *reinterpret_cast<const uint4*>(p.residual + off_);
                         }
                     }
                 }
-                uint32_t r[32];
-                tmem_ld_32x32(taddr0 + c, r);
-                tmem_ld_wait();
-                if (col0 < p.N) {  // warp-uniform
-                    // ---- this thread's row, 32 columns: bias, fp16 rounding, GELU (reference rounding points)
-                    float v[32];
+            };
+
+            if (splits == 1) {
+#pragma unroll 1
+                for (int c = 0; c < kColsPerWarp; c += 32) {
+                    uint4 resv[4];
+                    load_residual(resv, c);  // issued before the TMEM read so the latency hides behind it
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr0 + c, r);
+                    tmem_ld_wait();
+                    if (nt * BN + ch * kColsPerWarp + c < p.N) {  // warp-uniform
+                        float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (p.bias) {
-                        const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        finish_chunk(v, c, resv);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            } else {
+                // ---- split-K: park the raw fp32 tile, the last k slice to arrive adds the slices in order and finishes
+                float* wtile = p.sk_ws + ((size_t)tile * splits) * (kBlockM * BN);
+                const int trow = q * 32 + lane;
+                const bool row_ok = row_base + lane < p.rows_per_batch;  // rows past the batch are never stored
+#pragma unroll 1
+                for (int c = 0; c < kColsPerWarp; c += 32) {
+                    if (row_base >= p.rows_per_batch) break;  // warp-uniform: nothing of this quadrant is live
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr0 + c, r);
+                    tmem_ld_wait();
+                    if (!row_ok) continue;
+                    float4* dst = reinterpret_cast<float4*>(wtile + (size_t)ks * (kBlockM * BN) + (size_t)trow * BN + ch * kColsPerWarp + c);
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            uint4 bb = __ldg(bp + j4);
-                            const __half2* h2 = reinterpret_cast<const __half2*>(&bb);
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        dst[j4] = make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
+                                              __uint_as_float(r[4 * j4 + 3]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kEpiWarpsActive * 32) : "memory");
+                if (warp == kEpiWarp0 && lane == 0) {
+                    const unsigned old = atomicAdd(p.sk_cnt + tile, 1u);
+                    const bool last = (old == (unsigned)splits - 1u);
+                    if (last) p.sk_cnt[tile] = 0;  // ready for the next launch
+                    *sk_flag = last ? 1u : 0u;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kEpiWarpsActive * 32) : "memory");
+                const bool last = (*sk_flag != 0u);
+                asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kEpiWarpsActive * 32) : "memory");  // flag read by all before it is reused
+                if (last) {
+                    __threadfence();
+#pragma unroll 1
+                    for (int c = 0; c < kColsPerWarp; c += 32) {
+                        if (nt * BN + ch * kColsPerWarp + c >= p.N || row_base >= p.rows_per_batch) continue;
+                        uint4 resv[4];
+                        load_residual(resv, c);
+                        float v[32];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 f = __half22float2(h2[j]);
-                                v[j4 * 8 + 2 * j] += f.x;
-                                v[j4 * 8 + 2 * j + 1] += f.y;
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        for (int s_ = 0; s_ < splits && row_ok; ++s_) {
+                            const float4* src = reinterpret_cast<const float4*>(wtile + (size_t)s_ * (kBlockM * BN) + (size_t)trow * BN + ch * kColsPerWarp + c);
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 t = __ldcg(src + j4);
+                                v[4 * j4] += t.x;
+                                v[4 * j4 + 1] += t.y;
+                                v[4 * j4 + 2] += t.z;
+                                v[4 * j4 + 3] += t.w;
                             }
                         }
+                        finish_chunk(v, c, resv);
                     }
-                    if (p.flags & GEMM_GELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(round_f16(v[j]));
-                    }
-                    // ---- transpose through smem so that global accesses are 64 B contiguous per row
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        uint4 o;
-                        __half2* h2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(v[j4 * 8 + 2 * j], v[j4 * 8 + 2 * j + 1]);
-                        *reinterpret_cast<uint4*>(stg + lane * kStgRowBytes + j4 * 16) = o;
-                    }
-                    __syncwarp();
-                    const int piece = lane & 3;
-                    const int colp = col0 + piece * 8;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int rr = (lane >> 2) + 8 * i;
-                        const int grow = row_base + rr;
-                        if (grow < p.rows_per_batch && colp < p.N) {
-                            uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kStgRowBytes + piece * 16);
-                            long long off;
-                            if (p.flags & GEMM_HEADSPLIT) {
-                                off = ((long long)(b * p.hs_H + colp / 64) * p.hs_T + grow) * 64 + (colp % 64);
-                            } else {
-                                off = (long long)b * p.out_batch_stride + (long long)grow * p.out_row_stride + colp;
-                            }
-                            if (p.pos || p.residual) {
-                                __half2* h2 = reinterpret_cast<__half2*>(&val);
-                                float f[8];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float2 t = __half22float2(h2[j]);
-                                    f[2 * j] = t.x;
-                                    f[2 * j + 1] = t.y;
-                                }
-                                if (p.pos) {
-                                    const float4* pp = reinterpret_cast<const float4*>(p.pos + (long long)grow * p.N + colp);
-                                    const float4 a0 = __ldg(pp), a1 = __ldg(pp + 1);
-                                    f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
-                                    f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) f[j] = round_f16(f[j]);
-                                }
-                                if (p.residual) {
-                                    const uint4 rv = resv[i];
-                                    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        float2 t = __half22float2(rh[j]);
-                                        f[2 * j] += t.x;
-                                        f[2 * j + 1] += t.y;
-                                    }
-                                }
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-                            }
-                            if (colp + 8 <= p.N) {
-                                *reinterpret_cast<uint4*>(p.out + off) = val;
-                            } else {
-                                const __half* hv = reinterpret_cast<const __half*>(&val);
-                                for (int j = 0; j < 8 && colp + j < p.N; ++j) p.out[off + j] = hv[j];
-                            }
-                        }
-                    }
-                    __syncwarp();
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (warp == kEpiWarp0 && lane == 0 && item == (int)blockIdx.x) WJB_TRACE(7);
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -290,6 +406,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) WJB_TRACE(8);
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -334,6 +451,9 @@ int gemm_init() {
     return 0;
 }
 
+static unsigned long long* g_trace = nullptr;
+void gemm_set_trace(void* buf) { g_trace = reinterpret_cast<unsigned long long*>(buf); }
+
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     {
         static bool inited = false;
@@ -375,11 +495,30 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
         if (tiles_m * ((a.N + 63) / 64) * 2 <= sm_count()) bn = 32;
     }
     const int tiles = tiles_m * ((a.N + bn - 1) / bn);
+    d.trace = g_trace;
+    d.splits = 1;
+    d.sk_ws = nullptr;
+    d.sk_cnt = nullptr;
+    if (a.splits != 0 && a.splits != 1) {
+        if (!a.splitk_ws || !a.splitk_cnt) return set_error("gemm: split-K needs a workspace");
+        const int num_kb = (a.K + kBlockK - 1) / kBlockK;
+        int sp = a.splits > 1 ? a.splits : sm_count() / tiles;
+        if (sp > num_kb / 2) sp = num_kb / 2;  // at least two k blocks per slice
+        const size_t per_split = (size_t)tiles * kBlockM * bn * sizeof(float);
+        if (sp > 1 && per_split * sp > a.splitk_ws_bytes) sp = (int)(a.splitk_ws_bytes / per_split);
+        if (tiles > kSplitKCounters) sp = 1;
+        if (sp > 1) {
+            d.splits = sp;
+            d.sk_ws = a.splitk_ws;
+            d.sk_cnt = a.splitk_cnt;
+        }
+    }
+    const int items = tiles * d.splits;
     switch (bn) {
-        case 256: return launch_bn<256>(a, tmA, d, tiles, stream);
-        case 128: return launch_bn<128>(a, tmA, d, tiles, stream);
-        case 64: return launch_bn<64>(a, tmA, d, tiles, stream);
-        case 32: return launch_bn<32>(a, tmA, d, tiles, stream);
+        case 256: return launch_bn<256>(a, tmA, d, items, stream);
+        case 128: return launch_bn<128>(a, tmA, d, items, stream);
+        case 64: return launch_bn<64>(a, tmA, d, items, stream);
+        case 32: return launch_bn<32>(a, tmA, d, items, stream);
     }
     return set_error("gemm: unsupported block_n %d", bn);
 }

@@ -57,8 +57,16 @@ struct GemmArgs {
     int flags = 0;
     int hs_T = 0, hs_H = 0;
     int block_n = 0;                // 0 = auto
+    // split-K (few-row GEMMs that cannot fill the SMs with output tiles alone): 0/1 = off, > 1 = that many k slices,
+    // -1 = as many as fill the SMs. Needs a workspace that no concurrently running GEMM shares.
+    int splits = 0;
+    float* splitk_ws = nullptr;     // splitk_ws_bytes
+    size_t splitk_ws_bytes = 0;
+    unsigned* splitk_cnt = nullptr; // kSplitKCounters zeroed counters
 };
+constexpr int kSplitKCounters = 1024;
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+void gemm_set_trace(void* buf);  // debugging aid: device buffer of (8 + 256 * 32) u64 receiving CTA-0 timelines, null = off
 int gemm_init();  // set kernel attributes up front (outside any stream capture)
 // weight-streaming variant for <= 64 activation rows (decoder steps), gemm_skinny.cu
 int launch_gemm_skinny(const __half* x, int ldx, const __half* W, int ldw, const __half* bias, const __half* residual, __half* out,
