@@ -121,9 +121,18 @@ size_t wjb_gemm_splitk_workspace_bytes(void);
 int wjb_gemm_f16_splitk(const void* A, int64_t a_row_stride, int rows, int K, const void* W, int N, int ldw, const void* bias,
                         const void* residual, void* out, int64_t out_row_stride, int flags, int block_n, int splits,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* the decoder-step GEMM proper (rows <= 128, N % 64 == 0, K >= 512): a thread-block cluster of `cluster` CTAs (1|2|4|8,
+ * 0 = auto) slices K of one 128 x block_n (64|128|256, 0 = auto) output tile and the partial tiles meet in distributed shared
+ * memory, added in rank order.  w_constant = 1 promises W is not written by earlier work on the stream (model weights): its
+ * loads are then issued ahead of the programmatic-dependent-launch wait. */
+int wjb_gemm_step_f16(const void* A, int64_t a_row_stride, int rows, int K, const void* W, int N, int ldw, const void* bias,
+                      const void* residual, void* out, int64_t out_row_stride, int flags, int block_n, int cluster,
+                      int w_constant, void* stream);
 /* debugging aid: CTA 0 of every following GEMM launch writes a timeline (SM clock, global timer per pipeline event) into
- * `buf` (device, (32 + 256 * 32) uint64, zeroed by the caller); NULL switches it off. */
+ * `buf` (device, (32 + 512 * 32) uint64, zeroed by the caller; a ring of the last 512 launches); NULL switches it off. */
 void wjb_debug_gemm_trace(void* buf);
+/* debugging aid: launch the building blocks below with the programmatic-dependent-launch attribute, as the decode graph does */
+void wjb_debug_set_pdl(int on);
 /* tuning hook for the decode-step GEMM: columns per CTA = 8*nt (nt 1|2|4), ks = K slices per column group (cluster size);
  * 0 = built-in heuristic */
 void wjb_gemm_skinny_config(int nt, int ks);

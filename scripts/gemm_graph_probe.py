@@ -43,7 +43,7 @@ for name, (N, K) in {"n1280_k1280": (1280, 1280), "qkv_3840": (3840, 1280), "fc1
     b = torch.randn(N, device=DEV, dtype=torch.float16)
     out = torch.zeros(M, N, device=DEV, dtype=torch.float16)
     res[name] = {}
-    for bn in (32, 64, 128):
+    for bn in (32, 64):
         i = [0]
 
         def f():
@@ -51,17 +51,23 @@ for name, (N, K) in {"n1280_k1280": (1280, 1280), "qkv_3840": (3840, 1280), "fc1
             i[0] += 1
             _lib.check(lib.wjb_gemm_f16(_lib.ptr(A), K, 0, M, 1, K, _lib.ptr(W), N, K, _lib.ptr(b), None, _lib.ptr(out), N, 0, 0, bn, _lib.stream_ptr()), "tc")
         res[name][f"tc_bn{bn}"] = round(graph_time(f), 2)
-    ws_bytes = lib.wjb_gemm_splitk_workspace_bytes()
-    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=DEV)
-    for bn, sp in ((32, 2), (32, 3), (32, 4), (64, 2), (64, 3), (64, 4), (64, 7), (64, -1), (128, -1), (128, 4), (128, 7)):
-        i = [0]
+    for pdl in (0, 1):
+        lib.wjb_debug_set_pdl(pdl)
+        for bn, S in ((64, 2), (64, 4), (64, 8), (128, 2), (128, 4), (128, 8), (256, 2), (256, 4), (256, 8), (0, 0)):
+            if bn and (N // bn * S > 148 or K // 64 < S):
+                continue
+            i = [0]
 
-        def f():
-            W = Ws[i[0] % 8]
-            i[0] += 1
-            _lib.check(lib.wjb_gemm_f16_splitk(_lib.ptr(A), K, M, K, _lib.ptr(W), N, K, _lib.ptr(b), None, _lib.ptr(out), N, 0, bn, sp,
-                                               _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "tc split-K")
-        res[name][f"sk_bn{bn}_s{sp}"] = round(graph_time(f), 2)
+            def f():
+                W = Ws[i[0] % 8]
+                i[0] += 1
+                _lib.check(lib.wjb_gemm_step_f16(_lib.ptr(A), K, M, K, _lib.ptr(W), N, K, _lib.ptr(b), None, _lib.ptr(out), N, 0, bn, S, 1,
+                                                 _lib.stream_ptr()), "step")
+            try:
+                res[name][f"step_bn{bn}_s{S}_pdl{pdl}"] = round(graph_time(f), 2)
+            except Exception as e:  # a cluster shape the device cannot co-schedule
+                res[name][f"step_bn{bn}_s{S}_pdl{pdl}"] = str(e)[:60]
+    lib.wjb_debug_set_pdl(0)
     i = [0]
 
     def g():

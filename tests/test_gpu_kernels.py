@@ -110,6 +110,38 @@ def test_gemm_splitk_decode(lib, M, N, K, bn, splits):
         assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert int(ws[:4096].view(torch.int32).abs().sum().item()) == 0  # the counters are back at zero
 
+@pytest.mark.parametrize("M,N,K,bn,S", [(64, 1280, 1280, 0, 0), (64, 1280, 1280, 64, 4), (64, 1280, 1280, 128, 8), (64, 3840, 1280, 256, 8),
+                                        (33, 5120, 1280, 256, 4), (64, 1280, 5120, 128, 8), (1, 1280, 1280, 64, 2), (128, 1280, 2560, 0, 0),
+                                        (100, 384, 768, 64, 2), (128, 3840, 1280, 128, 4), (64, 5120, 1280, 0, 0), (7, 384, 512, 0, 0)])
+def test_gemm_step_cluster(lib, M, N, K, bn, S):
+    """Decoder-step GEMM: cluster split-K through distributed shared memory, every epilogue, in place residual, repeatable bits."""
+    g = torch.Generator().manual_seed(M + N + K + bn + S)
+    A = (torch.randn(M, K, generator=g)).half().to(DEV)
+    W = (torch.randn(N, K, generator=g) * 0.03).half().to(DEV)
+    bias = (torch.randn(N, generator=g) * 0.3).half().to(DEV)
+    res = (torch.randn(M, N, generator=g)).half().to(DEV)
+    lin = r16(A.float() @ W.float().t() + bias.float())
+    for flags, use_res, early in ((0, False, 0), (1, False, 1), (0, True, 1)):
+        outs = []
+        for rep in range(2):
+            out = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+            rbuf = None
+            if use_res:
+                out.copy_(res)
+                rbuf = out
+            _lib.check(lib.wjb_gemm_step_f16(_lib.ptr(A), K, M, K, _lib.ptr(W), N, K, _lib.ptr(bias), _lib.ptr(rbuf), _lib.ptr(out), N, flags, bn, S,
+                                             early, _lib.stream_ptr()), "step gemm")
+            torch.cuda.synchronize()
+            outs.append(out)
+        ref = lin
+        if flags:
+            ref = r16(torch.nn.functional.gelu(lin))
+        if use_res:
+            ref = r16(lin + res.float())
+        err = (outs[0].float() - ref).abs().max().item()
+        assert err <= 8e-3 * max(1.0, ref.abs().max().item() / 4), (flags, use_res, err)
+        assert torch.equal(outs[0], outs[1])
+
 
 @pytest.mark.parametrize("M,N,K", [(64, 1280, 1280), (64, 3840, 1280), (64, 1280, 5120), (1, 384, 384), (7, 51866, 384), (33, 5120, 1280)])
 def test_gemm_skinny_decode(lib, M, N, K):

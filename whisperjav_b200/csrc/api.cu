@@ -89,6 +89,7 @@ static int init_kernels() {
     static bool done = false;
     if (done) return 0;
     if (int e = gemm_init()) return e;
+    if (int e = gemm_step_init()) return e;
     if (int e = attn_init()) return e;
     if (int e = sample_init()) return e;
     done = true;
@@ -556,6 +557,25 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
             q.splitk_ws_bytes = kSplitKBytes;
         }
         if (skip & 2) return 0;
+        // default: the cluster split-K kernel written for exactly this shape class (gemm_step.cu)
+        static const bool use_step = !(getenv("WJB_DECODE_STEPGEMM") && atoi(getenv("WJB_DECODE_STEPGEMM")) == 0);
+        if (use_step && gemm_step_supported(B, N, K)) {
+            StepGemmArgs g;
+            g.A = A;
+            g.a_row_stride = K;
+            g.rows = B;
+            g.K = K;
+            g.W = W;
+            g.N = N;
+            g.ldw = ldw;
+            g.bias = bias;
+            g.residual = res;
+            g.out = out;
+            g.out_row_stride = out_stride;
+            g.flags = flags;
+            g.w_constant = true;
+            return launch_gemm_step(g, s);
+        }
         static const bool use_skinny = getenv("WJB_DECODE_SKINNY") != nullptr;
         if (use_skinny && B <= 64 && K % 32 == 0)
             return launch_gemm_skinny(A, K, W, ldw, bias, res, out, (int)out_stride, B, N, K, flags, s);
@@ -874,7 +894,34 @@ int wjb_gemm_f16(const void* A, int64_t a_row_stride, int64_t a_batch_stride, in
 
 size_t wjb_gemm_splitk_workspace_bytes(void) { return kSplitKSlot; }
 
-void wjb_debug_gemm_trace(void* buf) { gemm_set_trace(buf); }
+void wjb_debug_gemm_trace(void* buf) {
+    gemm_set_trace(buf);
+    gemm_step_set_trace(buf);
+}
+
+int wjb_gemm_step_f16(const void* A, int64_t a_row_stride, int rows, int K, const void* W, int N, int ldw, const void* bias,
+                      const void* residual, void* out, int64_t out_row_stride, int flags, int block_n, int cluster, int w_constant,
+                      void* stream) {
+    if (int e = init_kernels()) return e;
+    StepGemmArgs g;
+    g.A = (const __half*)A;
+    g.a_row_stride = a_row_stride;
+    g.rows = rows;
+    g.K = K;
+    g.W = (const __half*)W;
+    g.N = N;
+    g.ldw = ldw;
+    g.bias = (const __half*)bias;
+    g.residual = (const __half*)residual;
+    g.out = (__half*)out;
+    g.out_row_stride = out_row_stride;
+    g.flags = flags & GEMM_GELU;
+    g.block_n = block_n;
+    g.cluster = cluster;
+    g.w_constant = w_constant != 0;
+    return launch_gemm_step(g, (cudaStream_t)stream);
+}
+void wjb_debug_set_pdl(int on) { set_pdl(on != 0); }
 
 int wjb_gemm_f16_splitk(const void* A, int64_t a_row_stride, int rows, int K, const void* W, int N, int ldw, const void* bias,
                         const void* residual, void* out, int64_t out_row_stride, int flags, int block_n, int splits, void* workspace,

@@ -1,0 +1,444 @@
+// Decoder-step GEMM: out[r][n] = epilogue(sum_k A[r][k] W[n][k]) for <= 128 activation rows (one batch of decoder
+// rows), fp16 in, fp32 accumulate -- the Linear layers of openai-whisper model.py::ResidualAttentionBlock at one
+// autoregressive position.
+//
+// Such a GEMM is pure weight streaming, but one launch of the general tcgen05 kernel is bound by things that have
+// nothing to do with HBM (measured with the timeline hook, scripts/gemm_trace.py, and scripts/mma_rate.cu):
+//   * tcgen05.mma (M = 128, K = 16) costs 61 / 74 / 136 clk at N = 64 / 128 / 256 whether A comes from shared memory or
+//     from TMEM, but a tcgen05.commit between MMAs drains the pipe (~300 clk): with one commit per k block (needed to
+//     recycle a pipeline stage) a narrow tile runs at 300 ns per 64 columns of K, and K = 1280 costs 6 us per CTA,
+//   * an output-tile-only decomposition gives 20-80 CTAs that each re-read the whole activation block.
+// So here
+//   * a thread-block cluster of S CTAs shares one output tile (128 x BN) and slices K; the activation slice of a CTA
+//     arrives with one or two TMA loads (3-D box: 64 columns x rows x k blocks) and the weight slice is resident as a
+//     whole whenever it fits, so the k loop issues its MMAs back to back with a single commit at the end,
+//   * the fp32 partial tiles meet through distributed shared memory: CTA r owns BN/S columns, every CTA writes its
+//     partials of those columns into r's receive slab (st.shared::cluster, a warp writes 512 contiguous bytes), one
+//     cluster barrier, and r adds the S slabs in rank order (deterministic) and runs the epilogue (bias, GELU,
+//     residual) on its columns,
+//   * weights are constants, so their TMA loads are issued BEFORE griddepcontrol.wait: under programmatic dependent
+//     launch the CTAs of this GEMM are resident while the previous kernels of the step still run and the weight
+//     slices are already in shared memory when the activations become valid.
+#include "kernels.h"
+
+namespace wjb {
+
+constexpr int kStepThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..5 epilogue (TMEM lane quadrant = warp % 4)
+constexpr int kStepBlockK = 64;    // 128 B of fp16 per row: one SWIZZLE_128B atom
+constexpr int kStepMaxKb = 20;     // k blocks per CTA
+constexpr int kStepMaxStages = 20;
+constexpr int kStepSmemBudget = 216 * 1024;
+
+struct StepDev {
+    const __half* bias;
+    const __half* residual;
+    __half* out;
+    long long out_row_stride;
+    int rows, N, K, flags;
+    int a_tile;       // bytes of one activation k block in shared memory (TMA box rows x 128)
+    int a_chunks;     // TMA loads the activation slice arrives in (1 or 2)
+    int kpc;          // k blocks per such load
+    int w_stages;
+    int recv_rows;    // rows per receive slab (rows rounded up to 32)
+    int w_early;      // 1 = weights may be fetched before the previous kernel has finished
+    unsigned long long* trace;
+};
+
+#define WJB_STEP_TRACE(k)                                               \
+    do {                                                                \
+        if (trace_row) {                                                \
+            unsigned long long gt_;                                     \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));     \
+            trace_row[2 * (k)] = clock64();                             \
+            trace_row[2 * (k) + 1] = gt_;                               \
+        }                                                               \
+    } while (0)
+
+WJB_DEVINL uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+WJB_DEVINL uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+WJB_DEVINL void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+WJB_DEVINL void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+WJB_DEVINL uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+WJB_DEVINL void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kStepThreads, 1)
+gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const StepDev p) {
+    constexpr int kTmemCols = BN < 32 ? 32 : BN;
+    constexpr int kBBytes = BN * 128;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w_tiles = smem;                          // [w_stages][BN][128 B]              SWIZZLE_128B
+    uint8_t* a_tiles = smem + p.w_stages * kBBytes;   // [a_chunks * kpc][box rows][128 B]  SWIZZLE_128B, + 8 KB the MMA may over-read
+    float* recv = reinterpret_cast<float*>(a_tiles + p.a_chunks * p.kpc * p.a_tile + 8192);  // [S][BN / S / 4][recv_rows] float4
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(recv) + (size_t)p.recv_rows * BN * 4);
+    uint64_t* w_full = bars;
+    uint64_t* w_empty = w_full + kStepMaxStages;
+    uint64_t* a_full = w_empty + kStepMaxStages;  // one per activation load
+    uint64_t* tfull_bar = a_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t S = cluster_nctarank(), rank = cluster_ctarank();
+    const int nt = blockIdx.x / S;  // output tile (columns nt * BN ...)
+    const int num_kb_total = p.K / kStepBlockK;
+    const int kb0 = num_kb_total * (int)rank / (int)S, kb1 = num_kb_total * ((int)rank + 1) / (int)S;
+    const int nkb = kb1 - kb0;
+
+    __shared__ unsigned long long* trace_sh;
+    unsigned long long* trace_row = nullptr;
+    if (threadIdx.x == 0) {
+        if (p.trace && blockIdx.x == 0) {
+            const unsigned long long launch_idx = atomicAdd(p.trace, 1ull);
+            trace_row = p.trace + 32 + (launch_idx % 512) * 32;  // ring of the last 512 launches
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            trace_row[30] = smid;
+            trace_row[29] = launch_idx;
+            trace_row[28] = ((unsigned long long)p.N << 32) | (unsigned)p.K;
+            WJB_STEP_TRACE(0);
+        }
+        trace_sh = trace_row;
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < p.w_stages; ++s) {
+            mbar_init(&w_full[s], 1);
+            mbar_init(&w_empty[s], 1);
+        }
+        mbar_init(&a_full[0], 1);
+        mbar_init(&a_full[1], 1);
+        mbar_init(tfull_bar, 1);
+        fence_barrier_init();
+        // weight slices first: they neither depend on the previous kernel nor on TMEM
+        const int pre = p.w_early ? (nkb < p.w_stages ? nkb : p.w_stages) : 0;
+        for (int i = 0; i < pre; ++i) {
+            mbar_arrive_expect_tx(&w_full[i], kBBytes);
+            tma_load_2d(w_tiles + i * kBBytes, &tmB, &w_full[i], (kb0 + i) * kStepBlockK, nt * BN);
+        }
+        WJB_STEP_TRACE(1);
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    cluster_arrive();  // "this CTA is running": matched by the wait in front of the first remote store
+    const uint32_t tmem_base = *tmem_slot;
+    if (lane == 0) trace_row = trace_sh;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const int pre = p.w_early ? (nkb < p.w_stages ? nkb : p.w_stages) : 0;
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            WJB_STEP_TRACE(2);
+            for (int c = 0; c < p.a_chunks; ++c) {  // the whole activation slice: one 3-D box per load
+                mbar_arrive_expect_tx(&a_full[c], (uint32_t)(p.kpc * p.a_tile));
+                tma_load_3d(a_tiles + c * p.kpc * p.a_tile, &tmA, &a_full[c], 0, 0, kb0 + c * p.kpc);
+            }
+            WJB_STEP_TRACE(3);
+            int ws = pre % p.w_stages;
+            uint32_t wph = (pre / p.w_stages) & 1;
+            for (int i = pre; i < nkb; ++i) {
+                mbar_wait(&w_empty[ws], wph ^ 1);
+                mbar_arrive_expect_tx(&w_full[ws], kBBytes);
+                tma_load_2d(w_tiles + ws * kBBytes, &tmB, &w_full[ws], (kb0 + i) * kStepBlockK, nt * BN);
+                if (++ws == p.w_stages) {
+                    ws = 0;
+                    wph ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, BN, 0, 0);
+            int ws = 0;
+            uint32_t wph = 0;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(&w_full[ws], wph);
+                if (i % p.kpc == 0) mbar_wait(&a_full[i / p.kpc], 0);
+                tc_fence_after();
+                if (i == 0) WJB_STEP_TRACE(4);
+                if (i >= 1 && i <= 5) WJB_STEP_TRACE(8 + i);
+                // rows <= 64: the tile is 8 KB and the MMA's upper 64 rows read the next tile; their accumulator lanes are never used
+                const uint64_t da = make_smem_desc(smem_u32(a_tiles + i * p.a_tile), 16, 1024, kLayoutSW128);
+                const uint64_t db = make_smem_desc(smem_u32(w_tiles + ws * kBBytes), 16, 1024, kLayoutSW128);
+#pragma unroll
+                for (int k = 0; k < kStepBlockK / 16; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0);
+                // a commit drains the tensor pipe before the next MMA starts (~300 clk, scripts/mma_rate.cu): only pay for it when
+                // the weight stage is going to be refilled
+                if (i + p.w_stages < nkb) umma_commit(&w_empty[ws]);
+                if (++ws == p.w_stages) {
+                    ws = 0;
+                    wph ^= 1;
+                }
+            }
+            umma_commit(tfull_bar);
+            WJB_STEP_TRACE(5);
+        }
+    }
+    __syncwarp();
+
+    const int w = BN / (int)S;  // columns each CTA of the cluster finishes
+    if (warp >= 2) {
+        const int q = warp & 3;  // TMEM lane quadrant
+        const int row = q * 32 + lane;
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // the epilogue reads the residual and overwrites `out`
+        // ===================== partial tiles -> owners' receive slabs =====================
+        mbar_wait(tfull_bar, 0);
+        tc_fence_after();
+        if (warp == 2) WJB_STEP_TRACE(6);
+        cluster_wait();  // every CTA of the cluster is running: its shared memory may be written
+        if (q * 32 < p.rows) {
+            const uint32_t recv_local = smem_u32(recv);
+            const uint32_t qpo = (uint32_t)w / 4;  // float4 groups per owner
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + c, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const uint32_t g = (uint32_t)(c + j) / 4;  // float4 group of the tile
+                    const uint32_t owner = g / qpo, qd = g % qpo;
+                    // slab [source rank][group][row]: the 32 lanes of a store write 512 contiguous bytes
+                    const uint32_t off = ((rank * qpo + qd) * (uint32_t)p.recv_rows + (uint32_t)row) * 16;
+                    st_cluster_f4(map_to_rank(recv_local + off, owner), __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                  __uint_as_float(r[j + 3]));
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        cluster_wait();
+    }
+    cluster_arrive();
+    cluster_wait();  // all partials of my columns have landed
+    if (warp == 2) WJB_STEP_TRACE(7);
+
+    // ===================== add the S slabs in rank order, epilogue, store =====================
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64;  // 0..127
+        const int qpo = w / 4;
+        const int total = p.rows * qpo;
+        const int col_base = nt * BN + (int)rank * w;
+        const float4* slab = reinterpret_cast<const float4*>(recv);
+        for (int e = t; e < total; e += 128) {
+            const int row = e % p.rows, qd = e / p.rows;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (uint32_t s = 0; s < S; ++s) {
+                const float4 v = slab[((size_t)s * qpo + qd) * p.recv_rows + row];
+                acc.x += v.x;
+                acc.y += v.y;
+                acc.z += v.z;
+                acc.w += v.w;
+            }
+            const int col = col_base + qd * 4;
+            float v[4] = {acc.x, acc.y, acc.z, acc.w};
+            if (p.bias) {
+                const uint2 bb = __ldg(reinterpret_cast<const uint2*>(p.bias + col));
+                const __half2* h2 = reinterpret_cast<const __half2*>(&bb);
+                const float2 b0 = __half22float2(h2[0]), b1 = __half22float2(h2[1]);
+                v[0] += b0.x;
+                v[1] += b0.y;
+                v[2] += b1.x;
+                v[3] += b1.y;
+            }
+            if (p.flags & GEMM_GELU) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = gelu_erf_fast(round_f16(v[j]));
+            }
+            const long long off = (long long)row * p.out_row_stride + col;
+            if (p.residual) {
+                const uint2 rv = *reinterpret_cast<const uint2*>(p.residual + off);
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                const float2 r0 = __half22float2(rh[0]), r1 = __half22float2(rh[1]);
+                v[0] = round_f16(v[0]) + r0.x;  // the Linear output is an fp16 tensor before the residual add
+                v[1] = round_f16(v[1]) + r0.y;
+                v[2] = round_f16(v[2]) + r1.x;
+                v[3] = round_f16(v[3]) + r1.y;
+            }
+            uint2 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+            oh[0] = __floats2half2_rn(v[0], v[1]);
+            oh[1] = __floats2half2_rn(v[2], v[3]);
+            *reinterpret_cast<uint2*>(p.out + off) = o;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) WJB_STEP_TRACE(8);
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+static int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner,
+                     uint32_t box_outer) {
+    auto encode = get_tensor_map_encoder();
+    if (!encode) return set_error("cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("gemm_step: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+static unsigned long long* g_step_trace = nullptr;
+void gemm_step_set_trace(void* buf) { g_step_trace = reinterpret_cast<unsigned long long*>(buf); }
+
+static int encode_a_3d(CUtensorMap* map, const void* base, int K, int rows, long long row_stride_halfs, int box_rows, int kpc) {
+    auto encode = get_tensor_map_encoder();
+    if (!encode) return set_error("cuTensorMapEncodeTiled unavailable");
+    // [k block][row][64 halfs]: the k-block dimension is outermost in the box but has the smallest stride in memory
+    cuuint64_t dims[3] = {(cuuint64_t)kStepBlockK, (cuuint64_t)rows, (cuuint64_t)(K / kStepBlockK)};
+    cuuint64_t strides[2] = {(cuuint64_t)row_stride_halfs * 2, (cuuint64_t)kStepBlockK * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kStepBlockK, (cuuint32_t)box_rows, (cuuint32_t)kpc};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("gemm_step: cuTensorMapEncodeTiled (activations) failed (%d)", (int)r);
+    return 0;
+}
+
+// shared-memory plan of one configuration; false when it does not fit
+static bool plan_step(int rows, int K, int bn, int S, StepDev* d, size_t* smem_bytes) {
+    const int num_kb = K / kStepBlockK;
+    const int max_slice = (num_kb + S - 1) / S;
+    if (max_slice > kStepMaxKb || num_kb < S) return false;
+    const int box_rows = rows <= 64 ? 64 : 128;
+    d->a_tile = box_rows * 128;
+    d->a_chunks = max_slice >= 6 ? 2 : 1;
+    d->kpc = (max_slice + d->a_chunks - 1) / d->a_chunks;
+    d->recv_rows = (rows + 31) / 32 * 32;
+    const int recv_bytes = d->recv_rows * bn * 4;
+    const int a_bytes = d->a_chunks * d->kpc * d->a_tile + 8192;
+    int ws = (kStepSmemBudget - recv_bytes - a_bytes) / (bn * 128);
+    if (ws > max_slice) ws = max_slice;
+    if (ws > kStepMaxStages) ws = kStepMaxStages;
+    if (ws < 1 || (ws < 2 && max_slice >= 2)) return false;
+    d->w_stages = ws;
+    *smem_bytes = 1024 + (size_t)ws * bn * 128 + a_bytes + recv_bytes + (2 * kStepMaxStages + 4) * 8 + 64;
+    return true;
+}
+
+template <int BN>
+static int launch_step_bn(const StepGemmArgs& a, int S, cudaStream_t stream) {
+    StepDev d;
+    size_t smem = 0;
+    if (!plan_step(a.rows, a.K, BN, S, &d, &smem)) return set_error("gemm_step: rows=%d K=%d BN=%d S=%d does not fit shared memory", a.rows, a.K, BN, S);
+    d.bias = a.bias;
+    d.residual = a.residual;
+    d.out = a.out;
+    d.out_row_stride = a.out_row_stride;
+    d.rows = a.rows;
+    d.N = a.N;
+    d.K = a.K;
+    d.flags = a.flags;
+    d.w_early = a.w_constant ? 1 : 0;
+    d.trace = g_step_trace;
+    CUtensorMap tmA, tmB;
+    if (int e = encode_a_3d(&tmA, a.A, a.K, a.rows, a.a_row_stride, d.a_tile / 128, d.kpc)) return e;
+    if (int e = encode_2d(&tmB, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw * 2, kStepBlockK, (uint32_t)BN)) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((a.N / BN) * S);
+    cfg.blockDim = dim3(kStepThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = S;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_step_kernel<BN>, tmA, tmB, d);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("gemm_step launch (BN=%d S=%d smem=%zu): %s", BN, S, smem, cudaGetErrorString(e));
+    return 0;
+}
+
+int gemm_step_init() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(gemm_step_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBudget + 2048)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(gemm_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBudget + 2048)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(gemm_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBudget + 2048)) != cudaSuccess)
+        return set_error("gemm_step_init: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// Tile width / cluster size by a small cost model of the post-wait critical path (microseconds; constants measured with
+// scripts/mma_rate.cu and scripts/gemm_trace.py): weight k blocks that are not resident before the wait cost a TMA load each,
+// tcgen05.mma costs 61 / 74 / 136 clk at N = 64 / 128 / 256, distributed shared memory moves about 21 B/clk per SM.
+static bool pick_step_config(int rows, int N, int K, int* bn, int* S) {
+    float best = 1e30f;
+    for (int cand_bn : {64, 128, 256}) {
+        if (N % cand_bn) continue;
+        for (int cand_s : {8, 4, 2, 1}) {
+            StepDev d;
+            size_t smem;
+            if ((N / cand_bn) * cand_s > sm_count() || cand_bn / cand_s < 4 || !plan_step(rows, K, cand_bn, cand_s, &d, &smem)) continue;
+            const int slice = (K / kStepBlockK + cand_s - 1) / cand_s;
+            const float mma_clk = cand_bn == 64 ? 61.f : (cand_bn == 128 ? 74.f : 136.f);
+            const float t = 0.3f * (float)(slice > d.w_stages ? slice - d.w_stages : 0) + slice * 4 * mma_clk / 1900.f +
+                            (float)d.recv_rows * cand_bn * 4 * (cand_s - 1) / cand_s / (21.f * 1900.f) + (cand_s > 1 ? 0.4f : 0.f);
+            if (t < best) {
+                best = t;
+                *bn = cand_bn;
+                *S = cand_s;
+            }
+        }
+    }
+    return best < 1e29f;
+}
+
+// true when launch_gemm_step can take this problem (otherwise the caller uses the persistent kernel)
+bool gemm_step_supported(int rows, int N, int K) {
+    int bn, S;
+    return rows >= 1 && rows <= 128 && N % 64 == 0 && K % 64 == 0 && K >= 256 && pick_step_config(rows, N, K, &bn, &S);
+}
+
+int launch_gemm_step(const StepGemmArgs& a, cudaStream_t stream) {
+    if (!gemm_step_supported(a.rows, a.N, a.K)) return set_error("gemm_step: unsupported shape rows=%d N=%d K=%d", a.rows, a.N, a.K);
+    if (a.a_row_stride % 8 || a.ldw % 8) return set_error("gemm_step: strides must be multiples of 8 halfs");
+    int bn = a.block_n, S = a.cluster;
+    if (bn == 0 || S == 0) pick_step_config(a.rows, a.N, a.K, &bn, &S);
+    if (a.N % bn) return set_error("gemm_step: N=%d not a multiple of the tile width %d", a.N, bn);
+    if (S != 1 && S != 2 && S != 4 && S != 8) return set_error("gemm_step: cluster size %d", S);
+    if (bn / S < 4) return set_error("gemm_step: tile %d too narrow for %d slices", bn, S);
+    if ((a.K + kStepBlockK - 1) / kStepBlockK < S) return set_error("gemm_step: K=%d too short for %d slices", a.K, S);
+    if (a.out_row_stride % 4) return set_error("gemm_step: output row stride must be a multiple of 4 halfs");
+    switch (bn) {
+        case 64: return launch_step_bn<64>(a, S, stream);
+        case 128: return launch_step_bn<128>(a, S, stream);
+        case 256: return launch_step_bn<256>(a, S, stream);
+    }
+    return set_error("gemm_step: unsupported tile width %d", bn);
+}
+
+}  // namespace wjb

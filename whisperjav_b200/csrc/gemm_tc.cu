@@ -87,11 +87,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         unsigned long long* r = nullptr;
         if (blockIdx.x == 0) {
             const unsigned long long idx = atomicAdd(p.trace, 1ull);
-            if (idx < 256) r = p.trace + 32 + idx * 32;
-            if (r) {
+            r = p.trace + 32 + (idx % 512) * 32;  // ring of the last 512 launches
+            {
                 unsigned smid;
                 asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
                 r[30] = smid;
+                r[29] = idx;
+                r[28] = ((unsigned long long)p.N << 32) | (unsigned)p.K;
             }
         }
         trace_row_sh = r;

@@ -66,8 +66,29 @@ struct GemmArgs {
 };
 constexpr int kSplitKCounters = 1024;
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
-void gemm_set_trace(void* buf);  // debugging aid: device buffer of (8 + 256 * 32) u64 receiving CTA-0 timelines, null = off
+void gemm_set_trace(void* buf);  // debugging aid: device buffer of (32 + 512 * 32) u64 receiving CTA-0 timelines, null = off
 int gemm_init();  // set kernel attributes up front (outside any stream capture)
+// decoder-step variant (gemm_step.cu): <= 128 rows, a cluster of `cluster` CTAs slices K of one output tile and meets in
+// distributed shared memory; weights flagged constant are fetched ahead of the programmatic-dependent-launch wait
+struct StepGemmArgs {
+    const __half* A = nullptr;
+    long long a_row_stride = 0;
+    int rows = 0, K = 0;
+    const __half* W = nullptr;
+    int N = 0, ldw = 0;
+    const __half* bias = nullptr;
+    const __half* residual = nullptr;
+    __half* out = nullptr;
+    long long out_row_stride = 0;
+    int flags = 0;      // GEMM_GELU
+    int block_n = 0;    // 64 | 128 | 256, 0 = auto
+    int cluster = 0;    // 1 | 2 | 4 | 8, 0 = auto
+    bool w_constant = false;
+};
+bool gemm_step_supported(int rows, int N, int K);
+int launch_gemm_step(const StepGemmArgs& a, cudaStream_t stream);
+int gemm_step_init();
+void gemm_step_set_trace(void* buf);
 // weight-streaming variant for <= 64 activation rows (decoder steps), gemm_skinny.cu
 int launch_gemm_skinny(const __half* x, int ldx, const __half* W, int ldw, const __half* bias, const __half* residual, __half* out,
                        int ld_out, int M, int N, int K, int flags, cudaStream_t s);
