@@ -74,7 +74,4 @@ def run(N, K, bn, with_ln, pdl=0, S=None):
 
 print("step kernel slots: prologue=W issued, pdl_wait=released, tma0=first A issued, full0, mma_done=issued, acc_ready, stored=partials landed, exit")
 run(1280, 1280, 64, False, pdl=1, S=4)
-run(3840, 1280, 128, False, pdl=1, S=4)
-run(5120, 1280, 128, False, pdl=1, S=2)
 run(1280, 5120, 128, False, pdl=1, S=8)
-run(1280, 1280, 0, True, pdl=1, S=0)

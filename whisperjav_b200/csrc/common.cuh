@@ -61,6 +61,24 @@ WJB_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Whole-warp wait with a single polling lane: 32 lanes spinning on try_wait keep the barrier unit busy enough to slow down the
+// one thread that issues the MMAs; the warp barrier hands the acquired view to the other lanes.
+WJB_DEVINL void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) {
+        if (!mbar_try_wait(bar, parity)) {
+            const long long t0 = clock64();
+            while (!mbar_try_wait(bar, parity)) {
+                __nanosleep(40);
+                if (clock64() - t0 > 8000000000LL) {
+                    printf("wjb: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+                    __trap();
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------ TMA
 WJB_DEVINL void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

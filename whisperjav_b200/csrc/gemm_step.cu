@@ -167,25 +167,46 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16(128, BN, 0, 0);
-            int ws = 0;
-            uint32_t wph = 0;
-            for (int i = 0; i < nkb; ++i) {
-                mbar_wait(&w_full[ws], wph);
-                if (i % p.kpc == 0) mbar_wait(&a_full[i / p.kpc], 0);
+            if (p.w_stages >= nkb) {
+                // the whole weight slice is resident: collect every barrier first, then issue the MMAs back to back
+                // (a try_wait between groups of MMAs lets the tensor pipe run dry, scripts/mma_rate.cu)
+                for (int i = 0; i < nkb; ++i) mbar_wait(&w_full[i], 0);
+                mbar_wait(&a_full[0], 0);
                 tc_fence_after();
-                if (i == 0) WJB_STEP_TRACE(4);
-                if (i >= 1 && i <= 5) WJB_STEP_TRACE(8 + i);
-                // rows <= 64: the tile is 8 KB and the MMA's upper 64 rows read the next tile; their accumulator lanes are never used
-                const uint64_t da = make_smem_desc(smem_u32(a_tiles + i * p.a_tile), 16, 1024, kLayoutSW128);
-                const uint64_t db = make_smem_desc(smem_u32(w_tiles + ws * kBBytes), 16, 1024, kLayoutSW128);
+                WJB_STEP_TRACE(4);
+                for (int i = 0; i < nkb; ++i) {
+                    if (i == p.kpc) {
+                        mbar_wait(&a_full[1], 0);
+                        tc_fence_after();
+                    }
+                    if (i >= 1 && i <= 5) WJB_STEP_TRACE(8 + i);
+                    const uint64_t da = make_smem_desc(smem_u32(a_tiles + i * p.a_tile), 16, 1024, kLayoutSW128);
+                    const uint64_t db = make_smem_desc(smem_u32(w_tiles + i * kBBytes), 16, 1024, kLayoutSW128);
 #pragma unroll
-                for (int k = 0; k < kStepBlockK / 16; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0);
-                // a commit drains the tensor pipe before the next MMA starts (~300 clk, scripts/mma_rate.cu): only pay for it when
-                // the weight stage is going to be refilled
-                if (i + p.w_stages < nkb) umma_commit(&w_empty[ws]);
-                if (++ws == p.w_stages) {
-                    ws = 0;
-                    wph ^= 1;
+                    for (int k = 0; k < kStepBlockK / 16; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0);
+                }
+            } else {
+                int ws = 0;
+                uint32_t wph = 0;
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&w_full[ws], wph);
+                    if (i == 0) mbar_wait(&a_full[0], 0);
+                    if (i == p.kpc) mbar_wait(&a_full[1], 0);
+                    tc_fence_after();
+                    if (i == 0) WJB_STEP_TRACE(4);
+                    if (i >= 1 && i <= 5) WJB_STEP_TRACE(8 + i);
+                    // rows <= 64: the tile is 8 KB and the MMA's upper 64 rows read the next tile; their accumulator lanes are never used
+                    const uint64_t da = make_smem_desc(smem_u32(a_tiles + i * p.a_tile), 16, 1024, kLayoutSW128);
+                    const uint64_t db = make_smem_desc(smem_u32(w_tiles + ws * kBBytes), 16, 1024, kLayoutSW128);
+#pragma unroll
+                    for (int k = 0; k < kStepBlockK / 16; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0);
+                    // a commit drains the tensor pipe before the next MMA starts (~300 clk, scripts/mma_rate.cu): only pay for it
+                    // when the weight stage is going to be refilled
+                    if (i + p.w_stages < nkb) umma_commit(&w_empty[ws]);
+                    if (++ws == p.w_stages) {
+                        ws = 0;
+                        wph ^= 1;
+                    }
                 }
             }
             umma_commit(tfull_bar);
@@ -200,7 +221,7 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int row = q * 32 + lane;
         asm volatile("griddepcontrol.wait;" ::: "memory");  // the epilogue reads the residual and overwrites `out`
         // ===================== partial tiles -> owners' receive slabs =====================
-        mbar_wait(tfull_bar, 0);
+        mbar_wait_warp(tfull_bar, 0);
         tc_fence_after();
         if (warp == 2) WJB_STEP_TRACE(6);
         cluster_wait();  // every CTA of the cluster is running: its shared memory may be written

@@ -215,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int nt = tile % tiles_n, mt = tile / tiles_n;
             const int b = mt / m_tiles_per_batch;
             const int row_base = (mt % m_tiles_per_batch) * kBlockM + q * 32;  // first of this warp's 32 rows
-            mbar_wait(&tfull_bar[acc], acc_phase);
+            mbar_wait_warp(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             if (warp == kEpiWarp0 && lane == 0 && item == (int)blockIdx.x) WJB_TRACE(6);
             const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + ch * kColsPerWarp;
