@@ -7,6 +7,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
     python scripts/profile_step.py --batch 64 --tokens 4 > gpurun_out/prof_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc|attn_encoder|logmel_kernel|layernorm" -c 14 \
     -o gpurun_out/prof_encoder -f python scripts/profile_step.py --batch 64 --tokens 2 > gpurun_out/prof_enc.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"attn_dec|gemm_skinny|sample_kernel" -s 44 -c 12 \
+ncu --set full --clock-control none --import-source on -k regex:"attn_dec|gemm_step|sample_kernel" -s 44 -c 14 \
     -o gpurun_out/prof_decode -f python scripts/profile_step.py --batch 64 --tokens 3 > gpurun_out/prof_dec.log 2>&1
 ls -la gpurun_out/*.ncu-rep gpurun_out/launches.csv
