@@ -312,7 +312,7 @@ def run_ours(args):
         roofline = dict(rl_all[dominant])
     roofline["peak_source"] = peaks["source"] + (", sustained figure (kernel timed inside a long step)" if roofline["bound"] == "tensor" else "")
     tokens_out = int(np.mean([sum(len(r.tokens) for r in x["res"]) for x in extra]))
-    n_layers_launch = dims.n_text_layer * 12 + 5
+    n_layers_launch = dims.n_text_layer * 11 + 5  # per layer: 3 LN, 6 GEMM, self-, cross-attention; + embed, ln, logits, sample, advance
     gpu_launches = int(3 + gemm_launches + attn_launches + ln_launches + dims.n_text_layer + steps_run * n_layers_launch)
 
     out = None

@@ -139,6 +139,10 @@ void wjb_gemm_skinny_config(int nt, int ks);
 int wjb_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int n, void* stream);
 int wjb_attention_encoder_f16(const void* qkv, void* out, int batch, int T, int n_head, void* stream);
 /* single decoder step pieces */
+/* self-attention at *position (device int32): appends the k, v of qkv [B][3 * n_state] to kv_cache [B][2 * n_head][n_ctx][64]
+ * and attends over positions 0..*position */
+int wjb_attention_self_f16(const void* qkv, void* kv_cache, void* out, const int32_t* position, int batch, int n_head, int n_ctx,
+                           void* stream);
 int wjb_attention_cross_f16(const void* q, const void* kv, void* out, int batch, int n_head, int T, void* stream);
 
 /* ---- per-kernel-class timing of wjb_encoder_forward (CUDA events on the launching stream) ------

@@ -228,6 +228,30 @@ def test_attention_encoder(lib, diag_dir, B, T, H, scale):
     # fp16 P and fp16 output: a few 1e-3 absolute on O(1) values
     assert err <= tol, err
 
+@pytest.mark.parametrize("B,H,pos", [(2, 6, 0), (3, 6, 5), (64, 20, 226), (2, 1, 447), (5, 20, 63), (4, 6, 64)])
+def test_attention_self_decode(lib, B, H, pos):
+    """Decoder self-attention at one position: cache append + single-query attention over 0..pos."""
+    n, n_ctx = 64 * H, 448
+    g = torch.Generator().manual_seed(B + H + pos)
+    qkv = (torch.randn(B, 3 * n, generator=g) * 1.2).half().to(DEV)
+    cache = (torch.randn(B, 2 * H, n_ctx, 64, generator=g)).half().to(DEV)
+    before = cache.clone()
+    out = torch.empty(B, n, dtype=torch.float16, device=DEV)
+    p = torch.tensor([pos], dtype=torch.int32, device=DEV)
+    _lib.check(lib.wjb_attention_self_f16(_lib.ptr(qkv), _lib.ptr(cache), _lib.ptr(out), _lib.ptr(p), B, H, n_ctx, _lib.stream_ptr()), "self")
+    torch.cuda.synchronize()
+    k_new = qkv[:, n:2 * n].view(B, H, 64)
+    v_new = qkv[:, 2 * n:].view(B, H, 64)
+    assert torch.equal(cache[:, :H, pos], k_new) and torch.equal(cache[:, H:, pos], v_new)
+    keep = torch.ones(n_ctx, dtype=torch.bool)
+    keep[pos] = False
+    assert torch.equal(cache[:, :, keep], before[:, :, keep])  # nothing else is touched
+    q = qkv[:, :n].float().view(B, H, 1, 64)
+    k, v = cache[:, :H, : pos + 1].float(), cache[:, H:, : pos + 1].float()
+    w = r16(torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1))
+    ref = (w @ v).reshape(B, n)
+    assert (out.float() - ref).abs().max().item() <= 3e-3
+
 
 @pytest.mark.parametrize("B,H,T", [(2, 6, 1500), (64, 20, 1500), (3, 1, 100)])
 def test_attention_cross(lib, B, H, T):

@@ -960,6 +960,10 @@ int wjb_attention_encoder_f16(const void* qkv, void* out, int batch, int T, int 
     return launch_attn_encoder((const __half*)qkv, (__half*)out, batch, T, n_head, (cudaStream_t)stream);
 }
 
+int wjb_attention_self_f16(const void* qkv, void* kv_cache, void* out, const int32_t* position, int batch, int n_head, int n_ctx, void* stream) {
+    return launch_attn_dec_self((const __half*)qkv, (__half*)kv_cache, (__half*)out, position, nullptr, batch, n_head, n_ctx, (cudaStream_t)stream);
+}
+
 int wjb_attention_cross_f16(const void* q, const void* kv, void* out, int batch, int n_head, int T, void* stream) {
     return launch_attn_dec_cross((const __half*)q, (const __half*)kv, (__half*)out, nullptr, batch, n_head, T, (cudaStream_t)stream);
 }

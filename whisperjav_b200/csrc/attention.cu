@@ -276,82 +276,133 @@ int launch_attn_encoder(const __half* qkv, __half* out, int B, int T, int H, cud
 }
 
 // ============================================================================ decoder self-attention
-// One warp per (b, head).  kv_cache [B][2H][n_ctx][64]: K heads 0..H-1, V heads H..2H-1.
-__global__ void __launch_bounds__(32) attn_dec_self_kernel(const __half* __restrict__ qkv, __half* __restrict__ kv_cache,
-                                                           __half* __restrict__ out, const int* __restrict__ step_ptr,
-                                                           const unsigned char* __restrict__ done, int H, int n_ctx) {
+// One CTA (128 threads) per (b, head).  kv_cache [B][2H][n_ctx][64]: K heads 0..H-1, V heads H..2H-1.  Appends this
+// position's k, v, then single-query attention over positions 0..pos: 8 lanes x 16 B per cached row, 16 rows per pass and
+// 4 passes in flight per thread, so that at position 200+ the kernel is bound by cache bandwidth and not by one warp's
+// chain of dependent row loads (the first version, one warp per head, took 40 us per layer there).
+constexpr int kSelfThreads = 128;
+__global__ void __launch_bounds__(kSelfThreads) attn_dec_self_kernel(const __half* __restrict__ qkv, __half* __restrict__ kv_cache,
+                                                                      __half* __restrict__ out, const int* __restrict__ step_ptr,
+                                                                      const unsigned char* __restrict__ done, int H, int n_ctx) {
     pdl_prologue();
-    const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+    const int h = blockIdx.x, b = blockIdx.y;
     if (done && done[b]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pos = *step_ptr;
+    const int T = pos + 1;
     const int n = H * 64;
-    __shared__ float probs[448];
+    __shared__ float sc[448];
+    __shared__ float red[8];
+    __shared__ float osum[4][64];
     const __half* row = qkv + (long long)b * 3 * n;
-    __half* kc = kv_cache + ((long long)(b * 2 * H + h) * n_ctx) * 64;
-    __half* vc = kv_cache + ((long long)(b * 2 * H + H + h) * n_ctx) * 64;
-    // append this token's k, v
-    reinterpret_cast<__half2*>(kc + (long long)pos * 64)[lane] = reinterpret_cast<const __half2*>(row + n + h * 64)[lane];
-    reinterpret_cast<__half2*>(vc + (long long)pos * 64)[lane] = reinterpret_cast<const __half2*>(row + 2 * n + h * 64)[lane];
-    __syncwarp();
-    float q[64];
+    uint4* K = reinterpret_cast<uint4*>(kv_cache + ((long long)(b * 2 * H + h) * n_ctx) * 64);
+    uint4* V = reinterpret_cast<uint4*>(kv_cache + ((long long)(b * 2 * H + H + h) * n_ctx) * 64);
+    // append this token's k, v (8 x 16 B each)
+    if (tid < 8) K[(long long)pos * 8 + tid] = reinterpret_cast<const uint4*>(row + n + h * 64)[tid];
+    if (tid >= 8 && tid < 16) V[(long long)pos * 8 + tid - 8] = reinterpret_cast<const uint4*>(row + 2 * n + h * 64)[tid - 8];
+    const int chunk = tid & 7;  // which 16-byte (8 dims) slice of the 64-dim row
+    const int slot = tid >> 3;  // row slot 0..15 within a pass
+    float qf[8];
     {
-        const uint4* qp = reinterpret_cast<const uint4*>(row + h * 64);
+        uint4 u = reinterpret_cast<const uint4*>(row + h * 64)[chunk];
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            uint4 u = qp[i];
-            const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+        for (int j = 0; j < 4; ++j) {
+            float2 f = __half22float2(h2[j]);
+            qf[2 * j] = f.x;
+            qf[2 * j + 1] = f.y;
+        }
+    }
+    __syncthreads();  // the appended row is visible to the whole CTA
+    // ---- scores
+    for (int t0 = 0; t0 < T; t0 += 64) {
+        uint4 u[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int t = t0 + r * 16 + slot;
+            u[r] = (t < T) ? K[(long long)t * 8 + chunk] : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&u[r]);
+            float s = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float2 f = __half22float2(h2[j]);
-                q[i * 8 + 2 * j] = f.x;
-                q[i * 8 + 2 * j + 1] = f.y;
+                s = fmaf(qf[2 * j], f.x, s);
+                s = fmaf(qf[2 * j + 1], f.y, s);
             }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            const int t = t0 + r * 16 + slot;
+            if (chunk == 0 && t < T) sc[t] = s * 0.125f;
         }
     }
+    __syncthreads();
+    // ---- softmax over T scores
     float mx = -INFINITY;
-    for (int p = lane; p <= pos; p += 32) {
-        const uint4* kp = reinterpret_cast<const uint4*>(kc + (long long)p * 64);
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            uint4 u = kp[i];
-            const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float2 f = __half22float2(h2[j]);
-                s = fmaf(q[i * 8 + 2 * j], f.x, s);
-                s = fmaf(q[i * 8 + 2 * j + 1], f.y, s);
-            }
-        }
-        s *= 0.125f;
-        probs[p] = s;
-        mx = fmaxf(mx, s);
-    }
+    for (int t = tid; t < T; t += kSelfThreads) mx = fmaxf(mx, sc[t]);
     mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
     float sum = 0.f;
-    for (int p = lane; p <= pos; p += 32) {
-        const float e = __expf(probs[p] - mx);
-        probs[p] = e;
+    for (int t = tid; t < T; t += kSelfThreads) {
+        const float e = __expf(sc[t] - mx);
+        sc[t] = e;
         sum += e;
     }
     sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    __syncwarp();
-    float o0 = 0.f, o1 = 0.f;
-    for (int p = 0; p <= pos; ++p) {
-        const float w = round_f16(probs[p] * inv);
-        float2 v = __half22float2(reinterpret_cast<const __half2*>(vc + (long long)p * 64)[lane]);
-        o0 = fmaf(w, v.x, o0);
-        o1 = fmaf(w, v.y, o1);
+    if (lane == 0) red[4 + warp] = sum;
+    __syncthreads();
+    const float inv = 1.0f / (red[4] + red[5] + red[6] + red[7]);
+    // ---- out = sum_t p[t] V[t], p rounded to fp16 as the reference's softmax output is
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int t0 = 0; t0 < T; t0 += 64) {
+        uint4 u[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int t = t0 + r * 16 + slot;
+            u[r] = (t < T) ? V[(long long)t * 8 + chunk] : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int t = t0 + r * 16 + slot;
+            const float w = (t < T) ? round_f16(sc[t] * inv) : 0.f;
+            const __half2* h2 = reinterpret_cast<const __half2*>(&u[r]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h2[j]);
+                acc[2 * j] = fmaf(w, f.x, acc[2 * j]);
+                acc[2 * j + 1] = fmaf(w, f.y, acc[2 * j + 1]);
+            }
+        }
     }
-    reinterpret_cast<__half2*>(out + (long long)b * n + h * 64)[lane] = __floats2half2_rn(o0, o1);
+    // reduce over the 4 row slots inside a warp (lane bits 3,4), then over the 4 warps
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) osum[warp][lane * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const float v = osum[0][tid] + osum[1][tid] + osum[2][tid] + osum[3][tid];
+        out[(long long)b * n + h * 64 + tid] = __float2half_rn(v);
+    }
 }
 
 int launch_attn_dec_self(const __half* qkv, __half* kv_cache, __half* out, const int* step, const unsigned char* done, int B, int H,
                          int n_ctx, cudaStream_t s) {
     if (n_ctx > 448) return set_error("attn_dec_self: n_ctx %d > 448", n_ctx);
     dim3 grid(H, B);
-    launch_k(attn_dec_self_kernel, grid, dim3(32), 0, s, qkv, kv_cache, out, step, done, H, n_ctx);
+    launch_k(attn_dec_self_kernel, grid, dim3(kSelfThreads), 0, s, qkv, kv_cache, out, step, done, H, n_ctx);
     WJB_CHECK_LAUNCH("attn_dec_self");
     return 0;
 }
