@@ -128,6 +128,11 @@ int wjb_gemm_f16_splitk(const void* A, int64_t a_row_stride, int rows, int K, co
 int wjb_gemm_step_f16(const void* A, int64_t a_row_stride, int rows, int K, const void* W, int N, int ldw, const void* bias,
                       const void* residual, void* out, int64_t out_row_stride, int flags, int block_n, int cluster,
                       int w_constant, void* stream);
+/* the same with the LayerNorm in front of the Linear fused in (ln_gamma / ln_beta fp16 [K], eps 1e-5, fp32 statistics over the K
+ * columns of every row of A; both NULL = plain): the cluster exchanges per-row partial sums through distributed shared memory */
+int wjb_gemm_step_ln_f16(const void* A, int64_t a_row_stride, int rows, int K, const void* ln_gamma, const void* ln_beta,
+                         const void* W, int N, int ldw, const void* bias, const void* residual, void* out, int64_t out_row_stride,
+                         int flags, int block_n, int cluster, int w_constant, void* stream);
 /* debugging aid: CTA 0 of every following GEMM launch writes a timeline (SM clock, global timer per pipeline event) into
  * `buf` (device, (32 + 512 * 32) uint64, zeroed by the caller; a ring of the last 512 launches); NULL switches it off. */
 void wjb_debug_gemm_trace(void* buf);

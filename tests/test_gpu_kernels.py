@@ -142,6 +142,43 @@ def test_gemm_step_cluster(lib, M, N, K, bn, S):
         assert err <= 8e-3 * max(1.0, ref.abs().max().item() / 4), (flags, use_res, err)
         assert torch.equal(outs[0], outs[1])
 
+@pytest.mark.parametrize("M,N,K,bn,S", [(64, 3840, 1280, 0, 0), (64, 1280, 1280, 64, 4), (64, 5120, 1280, 0, 0), (33, 384, 384, 0, 0),
+                                        (128, 1280, 1280, 0, 0), (100, 1152, 384, 64, 2), (1, 1280, 1280, 128, 8), (64, 1280, 1280, 64, 1)])
+def test_gemm_step_fused_layernorm(lib, M, N, K, bn, S):
+    """LayerNorm + Linear in one launch (per-row statistics exchanged across the cluster) against LayerNorm -> fp16 -> Linear."""
+    g = torch.Generator().manual_seed(M + N + K + bn + S)
+    A = (torch.randn(M, K, generator=g) * 1.7 + 0.3).half().to(DEV)
+    W = (torch.randn(N, K, generator=g) * 0.03).half().to(DEV)
+    bias = (torch.randn(N, generator=g) * 0.3).half().to(DEV)
+    gamma = (1.0 + 0.2 * torch.randn(K, generator=g)).half().to(DEV)
+    beta = (0.1 * torch.randn(K, generator=g)).half().to(DEV)
+    res = (torch.randn(M, N, generator=g)).half().to(DEV)
+    h = r16(torch.nn.functional.layer_norm(A.float(), (K,), gamma.float(), beta.float(), 1e-5))
+    lin = r16(h @ W.float().t() + bias.float())
+    a_before = A.clone()
+    for flags, use_res in ((0, False), (1, False), (0, True)):
+        outs = []
+        for rep in range(2):
+            out = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+            rbuf = None
+            if use_res:
+                out.copy_(res)
+                rbuf = out
+            _lib.check(lib.wjb_gemm_step_ln_f16(_lib.ptr(A), K, M, K, _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(W), N, K, _lib.ptr(bias), _lib.ptr(rbuf),
+                                                _lib.ptr(out), N, flags, bn, S, 1, _lib.stream_ptr()), "step gemm + ln")
+            torch.cuda.synchronize()
+            outs.append(out)
+        ref = lin
+        if flags:
+            ref = r16(torch.nn.functional.gelu(lin))
+        if use_res:
+            ref = r16(lin + res.float())
+        err = (outs[0].float() - ref).abs().max().item()
+        # one fp16 ulp of a normalised activation (2^-10 at |h| ~ 2) times |W| summed over K stays well inside this
+        assert err <= 1.2e-2 * max(1.0, ref.abs().max().item() / 4), (flags, use_res, err)
+        assert torch.equal(outs[0], outs[1])
+    assert torch.equal(A, a_before)  # the residual stream itself is not touched
+
 
 @pytest.mark.parametrize("M,N,K", [(64, 1280, 1280), (64, 3840, 1280), (64, 1280, 5120), (1, 384, 384), (7, 51866, 384), (33, 5120, 1280)])
 def test_gemm_skinny_decode(lib, M, N, K):

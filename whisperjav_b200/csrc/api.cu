@@ -527,8 +527,12 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
     float* slp = slp0 + b0;
     float* nsp = nsp0 + b0;
     int32_t* out_len = out_len0 + b0;
+    // LayerNorm (ln_g/ln_b, may be null) followed by the Linear.  The step kernel can run the LayerNorm itself (one launch less,
+    // parity-tested), but its two cluster-wide exchanges cost more than the launch they save: 5.94 vs 5.58 ms/step measured,
+    // so the fusion is opt-in (WJB_DECODE_FUSE_LN=1)
+    static const bool fuse_ln = getenv("WJB_DECODE_FUSE_LN") && atoi(getenv("WJB_DECODE_FUSE_LN")) != 0;
     auto linear = [&](const __half* A, int K, const __half* W, int ldw, const __half* bias, const __half* res, __half* out, int N,
-                      long long out_stride, int flags) {
+                      long long out_stride, int flags, const __half* ln_g = nullptr, const __half* ln_b = nullptr) {
         GemmArgs q;
         q.A = A;
         q.a_row_stride = K;
@@ -574,7 +578,21 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
             g.out_row_stride = out_stride;
             g.flags = flags;
             g.w_constant = true;
+            if (ln_g && fuse_ln) {
+                g.ln_gamma = ln_g;
+                g.ln_beta = ln_b;
+                return launch_gemm_step(g, s);
+            }
+            if (ln_g) {  // LayerNorm as its own launch into w.h, then the Linear on it
+                if (!(skip & 1)) if (int e = launch_layernorm(A, ln_g, ln_b, w.h, B, K, s)) return e;
+                g.A = w.h;
+            }
             return launch_gemm_step(g, s);
+        }
+        if (ln_g) {
+            if (!(skip & 1)) if (int e = launch_layernorm(A, ln_g, ln_b, w.h, B, K, s)) return e;
+            q.A = w.h;
+            A = w.h;
         }
         static const bool use_skinny = getenv("WJB_DECODE_SKINNY") != nullptr;
         if (use_skinny && B <= 64 && K % 32 == 0)
@@ -586,17 +604,14 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
     const size_t cross_per_layer = (size_t)Btot * 2 * H * T * 64, cross_row = (size_t)2 * H * T * 64;
     for (int i = 0; i < d.n_text_layer; ++i) {
         const std::string p = "dec." + std::to_string(i) + ".";
-        if (!(skip & 1)) if (int e = launch_layernorm(w.x, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"), w.h, B, n, s)) return e;
-        if (int e = linear(w.h, n, m->h16(p + "qkv.w"), n, m->h16(p + "qkv.b"), nullptr, w.qkv, 3 * n, 3 * n, 0)) return e;
+        if (int e = linear(w.x, n, m->h16(p + "qkv.w"), n, m->h16(p + "qkv.b"), nullptr, w.qkv, 3 * n, 3 * n, 0, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"))) return e;
         if (!(skip & 4)) if (int e = launch_attn_dec_self(w.qkv, w.self_kv + i * self_per_layer + b0 * self_row, w.a, &w.ctl->step, w.done, B, H, d.n_text_ctx, s)) return e;
         if (int e = linear(w.a, n, m->h16(p + "out.w"), n, m->h16(p + "out.b"), w.x, w.x, n, n, 0)) return e;
-        if (!(skip & 1)) if (int e = launch_layernorm(w.x, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"), w.h, B, n, s)) return e;
-        if (int e = linear(w.h, n, m->h16(p + "cq.w"), n, m->h16(p + "cq.b"), nullptr, w.q, n, n, 0)) return e;
+        if (int e = linear(w.x, n, m->h16(p + "cq.w"), n, m->h16(p + "cq.b"), nullptr, w.q, n, n, 0, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"))) return e;
         if (!(skip & 8)) if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv0) + i * cross_per_layer + b0 * cross_row, w.a, w.done, B, H, T, s))
             return e;
         if (int e = linear(w.a, n, m->h16(p + "cout.w"), n, m->h16(p + "cout.b"), w.x, w.x, n, n, 0)) return e;
-        if (!(skip & 1)) if (int e = launch_layernorm(w.x, m->h16(p + "ln3.g"), m->h16(p + "ln3.b"), w.h, B, n, s)) return e;
-        if (int e = linear(w.h, n, m->h16(p + "fc1.w"), n, m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, 4 * n, GEMM_GELU)) return e;
+        if (int e = linear(w.x, n, m->h16(p + "fc1.w"), n, m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, 4 * n, GEMM_GELU, m->h16(p + "ln3.g"), m->h16(p + "ln3.b"))) return e;
         if (int e = linear(w.mlp, 4 * n, m->h16(p + "fc2.w"), 4 * n, m->h16(p + "fc2.b"), w.x, w.x, n, n, 0)) return e;
     }
     if (!(skip & 1)) if (int e = launch_layernorm(w.x, m->h16("dec.ln.g"), m->h16("dec.ln.b"), w.h, B, n, s)) return e;
@@ -899,9 +914,9 @@ void wjb_debug_gemm_trace(void* buf) {
     gemm_step_set_trace(buf);
 }
 
-int wjb_gemm_step_f16(const void* A, int64_t a_row_stride, int rows, int K, const void* W, int N, int ldw, const void* bias,
-                      const void* residual, void* out, int64_t out_row_stride, int flags, int block_n, int cluster, int w_constant,
-                      void* stream) {
+int wjb_gemm_step_ln_f16(const void* A, int64_t a_row_stride, int rows, int K, const void* ln_gamma, const void* ln_beta, const void* W, int N,
+                         int ldw, const void* bias, const void* residual, void* out, int64_t out_row_stride, int flags, int block_n,
+                         int cluster, int w_constant, void* stream) {
     if (int e = init_kernels()) return e;
     StepGemmArgs g;
     g.A = (const __half*)A;
@@ -919,7 +934,16 @@ int wjb_gemm_step_f16(const void* A, int64_t a_row_stride, int rows, int K, cons
     g.block_n = block_n;
     g.cluster = cluster;
     g.w_constant = w_constant != 0;
+    g.ln_gamma = (const __half*)ln_gamma;
+    g.ln_beta = (const __half*)ln_beta;
     return launch_gemm_step(g, (cudaStream_t)stream);
+}
+
+int wjb_gemm_step_f16(const void* A, int64_t a_row_stride, int rows, int K, const void* W, int N, int ldw, const void* bias,
+                      const void* residual, void* out, int64_t out_row_stride, int flags, int block_n, int cluster, int w_constant,
+                      void* stream) {
+    return wjb_gemm_step_ln_f16(A, a_row_stride, rows, K, nullptr, nullptr, W, N, ldw, bias, residual, out, out_row_stride, flags, block_n, cluster,
+                                w_constant, stream);
 }
 void wjb_debug_set_pdl(int on) { set_pdl(on != 0); }
 

@@ -16,6 +16,10 @@
 //     partials of those columns into r's receive slab (st.shared::cluster, a warp writes 512 contiguous bytes), one
 //     cluster barrier, and r adds the S slabs in rank order (deterministic) and runs the epilogue (bias, GELU,
 //     residual) on its columns,
+//   * optionally the LayerNorm in front of the Linear (model.py::ResidualAttentionBlock: attn_ln / cross_attn_ln / mlp_ln)
+//     runs inside: every CTA holds a K slice of all rows, so the cluster adds per-row partial sums through distributed
+//     shared memory (two passes: mean, then sum of squared deviations, fp32, rank order), normalises its tile in place
+//     and hands it to the MMA thread -- one launch and one global round trip less per LayerNorm,
 //   * weights are constants, so their TMA loads are issued BEFORE griddepcontrol.wait: under programmatic dependent
 //     launch the CTAs of this GEMM are resident while the previous kernels of the step still run and the weight
 //     slices are already in shared memory when the activations become valid.
@@ -41,6 +45,8 @@ struct StepDev {
     int w_stages;
     int recv_rows;    // rows per receive slab (rows rounded up to 32)
     int w_early;      // 1 = weights may be fetched before the previous kernel has finished
+    const __half* ln_g;  // LayerNorm over the K columns of every activation row, applied to the tile in shared memory before the
+    const __half* ln_b;  // MMAs (null = activations are used as they are)
     unsigned long long* trace;
 };
 
@@ -75,6 +81,8 @@ WJB_DEVINL void st_cluster_f4(uint32_t addr, float a, float b, float c, float d)
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+WJB_DEVINL void st_cluster_f1(uint32_t addr, float a) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory"); }
+
 template <int BN>
 __global__ void __launch_bounds__(kStepThreads, 1)
 gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const StepDev p) {
@@ -90,7 +98,10 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* w_empty = w_full + kStepMaxStages;
     uint64_t* a_full = w_empty + kStepMaxStages;  // one per activation load
     uint64_t* tfull_bar = a_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+    uint64_t* a_ready = tfull_bar + 1;  // LayerNorm variant: the normalised tile is in place
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+    float* lnbuf = reinterpret_cast<float*>(bars + 2 * kStepMaxStages + 8);  // [2 passes][S][128 rows] partial sums
+    const bool ln = p.ln_g != nullptr;
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,6 +134,7 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_init(&a_full[0], 1);
         mbar_init(&a_full[1], 1);
         mbar_init(tfull_bar, 1);
+        mbar_init(a_ready, 4);
         fence_barrier_init();
         // weight slices first: they neither depend on the previous kernel nor on TMEM
         const int pre = p.w_early ? (nkb < p.w_stages ? nkb : p.w_stages) : 0;
@@ -137,6 +149,7 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     cluster_arrive();  // "this CTA is running": matched by the wait in front of the first remote store
+    if (ln) cluster_wait();  // ... which in the LayerNorm variant is the exchange of partial sums, so wait right away
     const uint32_t tmem_base = *tmem_slot;
     if (lane == 0) trace_row = trace_sh;
 
@@ -151,6 +164,16 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_load_3d(a_tiles + c * p.kpc * p.a_tile, &tmA, &a_full[c], 0, 0, kb0 + c * p.kpc);
             }
             WJB_STEP_TRACE(3);
+        }
+        __syncwarp();
+        if (ln) {  // every thread of the cluster takes part in the two partial-sum exchanges
+            cluster_arrive();
+            cluster_wait();
+            cluster_arrive();
+            cluster_wait();
+        }
+        if (lane == 0) {
+            const int pre = p.w_early ? (nkb < p.w_stages ? nkb : p.w_stages) : 0;
             int ws = pre % p.w_stages;
             uint32_t wph = (pre / p.w_stages) & 1;
             for (int i = pre; i < nkb; ++i) {
@@ -165,8 +188,19 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        if (ln) {
+            cluster_arrive();
+            cluster_wait();
+            cluster_arrive();
+            cluster_wait();
+        }
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16(128, BN, 0, 0);
+            if (ln) {  // activation barriers first, then the normalised tile
+                mbar_wait(&a_full[0], 0);
+                if (p.a_chunks > 1) mbar_wait(&a_full[1], 0);
+                mbar_wait(a_ready, 0);
+            }
             if (p.w_stages >= nkb) {
                 // the whole weight slice is resident: collect every barrier first, then issue the MMAs back to back
                 // (a try_wait between groups of MMAs lets the tensor pipe run dry, scripts/mma_rate.cu)
@@ -220,11 +254,84 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;  // TMEM lane quadrant
         const int row = q * 32 + lane;
         asm volatile("griddepcontrol.wait;" ::: "memory");  // the epilogue reads the residual and overwrites `out`
+        if (ln) {
+            // ===================== LayerNorm of the activation tile, in place =====================
+            // rows <= 64: two threads per row (4 of the 8 16-byte chunks of a k block each), else one thread per row
+            const int t = threadIdx.x - 64;
+            const int tpr = p.rows <= 64 ? 2 : 1;
+            const int lrow = t / tpr, part = t % tpr;
+            const bool active = lrow < p.rows;
+            const int c0 = part * (8 / tpr), c1 = c0 + 8 / tpr;
+            const uint32_t lnbuf_local = smem_u32(lnbuf);
+            mbar_wait_warp(&a_full[0], 0);
+            if (p.a_chunks > 1) mbar_wait_warp(&a_full[1], 0);
+            const uint8_t* rbase = a_tiles + lrow * 128;
+            float mean = 0.f, rstd = 0.f;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                float acc = 0.f;
+                if (active) {
+                    for (int i = 0; i < nkb; ++i) {
+                        for (int j = c0; j < c1; ++j) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(rbase + i * p.a_tile + ((j ^ (lrow & 7)) << 4));
+                            const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(h2[e]);
+                                if (pass == 0) {
+                                    acc += f.x + f.y;
+                                } else {
+                                    const float d0 = f.x - mean, d1 = f.y - mean;
+                                    acc += d0 * d0 + d1 * d1;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (tpr == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                if (active && part == 0) {
+                    const uint32_t off = ((uint32_t)(pass * 8 + (int)rank) * 128 + (uint32_t)lrow) * 4;
+                    for (uint32_t dst = 0; dst < S; ++dst) st_cluster_f1(map_to_rank(lnbuf_local + off, dst), acc);
+                }
+                cluster_arrive();
+                cluster_wait();
+                float tot = 0.f;
+                if (active)
+                    for (uint32_t sr = 0; sr < S; ++sr) tot += lnbuf[(pass * 8 + sr) * 128 + lrow];
+                if (pass == 0)
+                    mean = tot / (float)p.K;
+                else
+                    rstd = rsqrtf(tot / (float)p.K + 1e-5f);
+            }
+            if (active) {
+                for (int i = 0; i < nkb; ++i) {
+                    for (int j = c0; j < c1; ++j) {
+                        uint4* px = reinterpret_cast<uint4*>(const_cast<uint8_t*>(rbase) + i * p.a_tile + ((j ^ (lrow & 7)) << 4));
+                        uint4 u = *px;
+                        const long long kcol = (long long)(kb0 + i) * kStepBlockK + j * 8;
+                        const uint4 g = __ldg(reinterpret_cast<const uint4*>(p.ln_g + kcol));
+                        const uint4 bb = __ldg(reinterpret_cast<const uint4*>(p.ln_b + kcol));
+                        __half2* h2 = reinterpret_cast<__half2*>(&u);
+                        const __half2* gh = reinterpret_cast<const __half2*>(&g);
+                        const __half2* bh = reinterpret_cast<const __half2*>(&bb);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __half22float2(h2[e]), gf = __half22float2(gh[e]), bf = __half22float2(bh[e]);
+                            h2[e] = __floats2half2_rn((f.x - mean) * rstd * gf.x + bf.x, (f.y - mean) * rstd * gf.y + bf.y);
+                        }
+                        *px = u;
+                    }
+                }
+            }
+            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's reads of shared memory
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+        }
         // ===================== partial tiles -> owners' receive slabs =====================
         mbar_wait_warp(tfull_bar, 0);
         tc_fence_after();
         if (warp == 2) WJB_STEP_TRACE(6);
-        cluster_wait();  // every CTA of the cluster is running: its shared memory may be written
+        if (!ln) cluster_wait();  // every CTA of the cluster is running: its shared memory may be written
         if (q * 32 < p.rows) {
             const uint32_t recv_local = smem_u32(recv);
             const uint32_t qpo = (uint32_t)w / 4;  // float4 groups per owner
@@ -245,7 +352,7 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
         tc_fence_before();
-    } else {
+    } else if (!ln) {
         cluster_wait();
     }
     cluster_arrive();
@@ -352,12 +459,12 @@ static bool plan_step(int rows, int K, int bn, int S, StepDev* d, size_t* smem_b
     d->recv_rows = (rows + 31) / 32 * 32;
     const int recv_bytes = d->recv_rows * bn * 4;
     const int a_bytes = d->a_chunks * d->kpc * d->a_tile + 8192;
-    int ws = (kStepSmemBudget - recv_bytes - a_bytes) / (bn * 128);
+    int ws = (kStepSmemBudget - 8192 /*LayerNorm partial sums*/ - recv_bytes - a_bytes) / (bn * 128);
     if (ws > max_slice) ws = max_slice;
     if (ws > kStepMaxStages) ws = kStepMaxStages;
     if (ws < 1 || (ws < 2 && max_slice >= 2)) return false;
     d->w_stages = ws;
-    *smem_bytes = 1024 + (size_t)ws * bn * 128 + a_bytes + recv_bytes + (2 * kStepMaxStages + 4) * 8 + 64;
+    *smem_bytes = 1024 + (size_t)ws * bn * 128 + a_bytes + recv_bytes + (2 * kStepMaxStages + 8) * 8 + 2 * 8 * 128 * 4 + 64;
     return true;
 }
 
@@ -375,6 +482,8 @@ static int launch_step_bn(const StepGemmArgs& a, int S, cudaStream_t stream) {
     d.K = a.K;
     d.flags = a.flags;
     d.w_early = a.w_constant ? 1 : 0;
+    d.ln_g = a.ln_gamma;
+    d.ln_b = a.ln_beta;
     d.trace = g_step_trace;
     CUtensorMap tmA, tmB;
     if (int e = encode_a_3d(&tmA, a.A, a.K, a.rows, a.a_row_stride, d.a_tile / 128, d.kpc)) return e;
@@ -454,6 +563,7 @@ int launch_gemm_step(const StepGemmArgs& a, cudaStream_t stream) {
     if (bn / S < 4) return set_error("gemm_step: tile %d too narrow for %d slices", bn, S);
     if ((a.K + kStepBlockK - 1) / kStepBlockK < S) return set_error("gemm_step: K=%d too short for %d slices", a.K, S);
     if (a.out_row_stride % 4) return set_error("gemm_step: output row stride must be a multiple of 4 halfs");
+    if ((a.ln_gamma == nullptr) != (a.ln_beta == nullptr)) return set_error("gemm_step: LayerNorm needs both gamma and beta");
     switch (bn) {
         case 64: return launch_step_bn<64>(a, S, stream);
         case 128: return launch_step_bn<128>(a, S, stream);

@@ -84,6 +84,8 @@ struct StepGemmArgs {
     int block_n = 0;    // 64 | 128 | 256, 0 = auto
     int cluster = 0;    // 1 | 2 | 4 | 8, 0 = auto
     bool w_constant = false;
+    const __half* ln_gamma = nullptr;  // LayerNorm over the K columns of A applied inside the kernel (both or neither)
+    const __half* ln_beta = nullptr;
 };
 bool gemm_step_supported(int rows, int N, int K);
 int launch_gemm_step(const StepGemmArgs& a, cudaStream_t stream);
