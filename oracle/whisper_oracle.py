@@ -6,7 +6,8 @@ Each function names the upstream file it follows (upstream is *not* vendored in
 
 * ``log_mel_spectrogram`` / ``pad_or_trim`` / ``mel_filters``   <- whisper/audio.py
 * ``sinusoids`` / ``encoder_forward`` / ``decoder_forward``      <- whisper/model.py
-* ``DecodingOptions`` / ``decode`` (greedy, logit filters)       <- whisper/decoding.py
+* ``DecodingOptions`` / ``decode`` (greedy, logit filters),
+  ``BeamSearch`` / ``decode_beam`` / ``rank_maximum_likelihood`` <- whisper/decoding.py
 * ``transcribe`` (seek loop, thresholds, timestamp slicing)      <- whisper/transcribe.py
 
 ``sim_fp16=True`` reproduces the rounding points of the reference's fp16 GPU run
@@ -476,8 +477,12 @@ def decode(weights, dims: ModelDimensions, mel: torch.Tensor, options: DecodingO
     """decoding.py::DecodingTask.run for greedy decoding (``beam_size is None``, T == 0).
 
     mel [B, n_mels, 3000] (or pre-computed ``audio_features`` [B, 1500, n_state])."""
-    if options.beam_size is not None or (options.best_of or 1) > 1:
-        raise NotImplementedError("oracle covers greedy decoding (north_star's graded mode)")
+    if options.beam_size is not None:
+        if return_logits:
+            raise NotImplementedError("return_logits is a greedy-path diagnostic")
+        return decode_beam(weights, dims, mel, options, sim_fp16, audio_features)
+    if (options.best_of or 1) > 1:
+        raise NotImplementedError("oracle covers greedy and beam-search decoding; sampling is checked statistically on the device path")
     if options.temperature != 0.0:
         raise NotImplementedError("oracle covers temperature 0 only")
     tok = SpecialTokens(dims.n_vocab, language=options.language or "en", task=options.task)
@@ -543,6 +548,162 @@ def decode(weights, dims: ModelDimensions, mel: torch.Tensor, options: DecodingO
     return results
 
 
+class BeamSearch:
+    """decoding.py::BeamSearchDecoder restated on plain tensors: ``update`` consumes the filtered logits of every beam row
+    and returns the kept sequences plus the row each one continues (upstream calls ``inference.rearrange_kv_cache`` with
+    those indices), ``finalize`` tops the finished lists up from the live beams.  Ranking of equal scores follows the
+    insertion order of upstream's dicts (beam index, then top-k order) because ``sorted`` is stable.
+
+    Parity status: restated from openai-whisper 20250625 @ c0d2f62, which is absent from this container -> unpinned against
+    the reference itself; pinned only through properties (tests/test_oracle_beam.py)."""
+
+    def __init__(self, beam_size: int, eot: int, patience: Optional[float] = None):
+        self.beam_size = beam_size
+        self.eot = eot
+        self.patience = patience or 1.0
+        self.max_candidates = round(beam_size * self.patience)
+        self.finished_sequences: Optional[List[Dict[Tuple[int, ...], float]]] = None
+        assert self.max_candidates > 0, f"Invalid beam size ({beam_size}) or patience ({patience})"
+
+    def reset(self):
+        self.finished_sequences = None
+
+    def update(self, tokens: torch.Tensor, logits: torch.Tensor, sum_logprobs: torch.Tensor):
+        if tokens.shape[0] % self.beam_size != 0:
+            raise ValueError(f"{tokens.shape}[0] % {self.beam_size} != 0")
+        n_audio = tokens.shape[0] // self.beam_size
+        if self.finished_sequences is None:
+            self.finished_sequences = [{} for _ in range(n_audio)]
+        logprobs = F.log_softmax(logits.float(), dim=-1)
+        next_tokens, source_indices, finished_sequences = [], [], []
+        for i in range(n_audio):
+            scores, sources, finished = {}, {}, {}
+            # STEP 1: cumulative log probabilities of the candidates of every beam (identical beams collapse: dict keys)
+            for j in range(self.beam_size):
+                idx = i * self.beam_size + j
+                prefix = tokens[idx].tolist()
+                for logprob, token in zip(*logprobs[idx].topk(self.beam_size + 1)):
+                    new_logprob = (sum_logprobs[idx] + logprob).item()
+                    sequence = tuple(prefix + [token.item()])
+                    scores[sequence] = new_logprob
+                    sources[sequence] = idx
+            # STEP 2: rank the candidates, keep the top beam_size live ones; EOT-terminated ones passed on the way finish
+            saved = 0
+            for sequence in sorted(scores, key=scores.get, reverse=True):
+                if sequence[-1] == self.eot:
+                    finished[sequence] = scores[sequence]
+                else:
+                    sum_logprobs[len(next_tokens)] = scores[sequence]
+                    next_tokens.append(sequence)
+                    source_indices.append(sources[sequence])
+                    saved += 1
+                    if saved == self.beam_size:
+                        break
+            finished_sequences.append(finished)
+        tokens = torch.tensor(next_tokens)
+        for previously_finished, newly_finished in zip(self.finished_sequences, finished_sequences):
+            for seq in sorted(newly_finished, key=newly_finished.get, reverse=True):
+                if len(previously_finished) >= self.max_candidates:
+                    break  # the candidate list is full
+                previously_finished[seq] = newly_finished[seq]
+        completed = all(len(sequences) >= self.max_candidates for sequences in self.finished_sequences)
+        return tokens, source_indices, completed
+
+    def finalize(self, preceding_tokens: torch.Tensor, sum_logprobs: torch.Tensor):
+        """preceding_tokens [n_audio, beam, T], sum_logprobs [n_audio, beam]."""
+        sum_logprobs = sum_logprobs.cpu()
+        for i, sequences in enumerate(self.finished_sequences):
+            if len(sequences) < self.beam_size:  # not enough finished: take the best live beams, EOT appended
+                for j in list(np.argsort(sum_logprobs[i].numpy()))[::-1]:
+                    sequence = preceding_tokens[i, j].tolist() + [self.eot]
+                    sequences[tuple(sequence)] = sum_logprobs[i][j].item()
+                    if len(sequences) >= self.beam_size:
+                        break
+        tokens = [[torch.tensor(seq) for seq in sequences.keys()] for sequences in self.finished_sequences]
+        sums = [list(sequences.values()) for sequences in self.finished_sequences]
+        return tokens, sums
+
+
+def rank_maximum_likelihood(tokens: List[List[torch.Tensor]], sum_logprobs: List[List[float]],
+                            length_penalty: Optional[float] = None) -> List[int]:
+    """decoding.py::MaximumLikelihoodRanker.rank: per audio the candidate with the best length-normalised log probability
+    (``logprob / length``, or the Google NMT penalty ``((5 + length) / 6) ** length_penalty``)."""
+
+    def scores(logprobs, lengths):
+        result = []
+        for logprob, length in zip(logprobs, lengths):
+            penalty = length if length_penalty is None else ((5 + length) / 6) ** length_penalty
+            result.append(logprob / penalty)
+        return result
+
+    lengths = [[len(t) for t in s] for s in tokens]
+    return [int(np.argmax(scores(p, l))) for p, l in zip(sum_logprobs, lengths)]
+
+
+def decode_beam(weights, dims: ModelDimensions, mel: torch.Tensor, options: DecodingOptions, sim_fp16: bool = True,
+                audio_features: Optional[torch.Tensor] = None) -> List[DecodingResult]:
+    """decoding.py::DecodingTask.run with ``beam_size`` set (T == 0): audio features and tokens repeated per beam, the logit
+    filters applied per row, BeamSearchDecoder.update + KV-cache rearrangement every step, finalize, MaximumLikelihoodRanker."""
+    if options.temperature != 0.0:
+        raise NotImplementedError("beam search runs at temperature 0 (transcribe drops beam_size when t > 0)")
+    n_group = options.beam_size
+    tok = SpecialTokens(dims.n_vocab, language=options.language or "en", task=options.task)
+    n_ctx = dims.n_text_ctx
+    sample_len = options.sample_len or n_ctx // 2
+    initial_tokens = get_initial_tokens(tok, options, n_ctx)
+    sample_begin = len(initial_tokens)
+    sot_index = initial_tokens.index(tok.sot)
+    suppress = get_suppress_tokens(tok, options) if options.suppress_tokens else ()
+    max_initial_timestamp_index = None
+    if not options.without_timestamps and options.max_initial_timestamp:
+        precision = CHUNK_LENGTH / dims.n_audio_ctx
+        max_initial_timestamp_index = round(options.max_initial_timestamp / precision)
+    if audio_features is None:
+        audio_features = encoder_forward(weights, dims, mel, sim_fp16)
+    n_audio = audio_features.shape[0]
+    tokens = torch.tensor([initial_tokens]).repeat(n_audio, 1)
+    # repeat text tensors by the group size
+    tokens = tokens.repeat_interleave(n_group, dim=0)
+    xa = audio_features.repeat_interleave(n_group, dim=0)
+    n_batch = tokens.shape[0]
+    sum_logprobs = torch.zeros(n_batch)
+    no_speech_probs = [np.nan] * n_batch
+    state = DecoderState()
+    beam = BeamSearch(n_group, tok.eot, options.patience)
+    for i in range(sample_len):
+        inp = tokens if i == 0 else tokens[:, -1:]
+        logits = decoder_forward(weights, dims, inp, xa, state, sim_fp16)
+        if i == 0:
+            probs_at_sot = logits[:, sot_index].float().softmax(dim=-1)
+            no_speech_probs = probs_at_sot[:, tok.no_speech].tolist()
+        logits = logits[:, -1]
+        apply_logit_filters(logits, tokens, tok, options, sample_begin, suppress, max_initial_timestamp_index)
+        tokens, source_indices, completed = beam.update(tokens, logits, sum_logprobs)
+        # PyTorchInference.rearrange_kv_cache: self-attention caches follow their beams (cross K/V rows of one audio are equal)
+        if source_indices != list(range(len(source_indices))):
+            idx = torch.tensor(source_indices)
+            for layer in list(state.self_k):
+                state.self_k[layer] = state.self_k[layer][idx]
+                state.self_v[layer] = state.self_v[layer][idx]
+        if completed or tokens.shape[-1] > n_ctx:
+            break
+    no_speech_probs = no_speech_probs[::n_group]
+    tokens = tokens.reshape(n_audio, n_group, -1)
+    sum_logprobs = sum_logprobs.reshape(n_audio, n_group)
+    cand_tokens, cand_sums = beam.finalize(tokens, sum_logprobs)
+    cand_tokens = [[t[sample_begin: int((t == tok.eot).nonzero()[0, 0])] for t in s] for s in cand_tokens]
+    selected = rank_maximum_likelihood(cand_tokens, cand_sums, options.length_penalty)
+    results = []
+    for b in range(n_audio):
+        out = cand_tokens[b][selected[b]].tolist()
+        slp = float(cand_sums[b][selected[b]])
+        text = placeholder_detokenize([x for x in out if x < tok.eot]).strip()
+        results.append(DecodingResult(tokens=out, text=text, avg_logprob=slp / (len(out) + 1), no_speech_prob=float(no_speech_probs[b]),
+                                      temperature=options.temperature, compression_ratio=compression_ratio(text) if text else 0.0,
+                                      language=options.language or "en", sum_logprob=slp))
+    return results
+
+
 # ----------------------------------------------------------------------------- transcribe.py
 def slice_segments(tokens: List[int], tok: SpecialTokens, seek: int, segment_size: int,
                    result_fields: dict, detok=placeholder_detokenize):
@@ -597,7 +758,7 @@ def transcribe(weights, dims: ModelDimensions, audio: np.ndarray, *, task="trans
                no_speech_threshold=0.6, condition_on_previous_text=True, sim_fp16=True,
                **decode_options) -> dict:
     """transcribe.py::transcribe (word_timestamps=False, clip_timestamps="0", language given).
-    One audio array -> {"text", "segments", "language"}.  Greedy only (see ``decode``)."""
+    One audio array -> {"text", "segments", "language"}.  Greedy or beam search at t == 0 (see ``decode``)."""
     decode_options = {k: v for k, v in decode_options.items() if k not in ("verbose", "word_timestamps", "fp16")}
     mel = log_mel_spectrogram(audio, dims.n_mels, padding=N_SAMPLES)
     content_frames = mel.shape[-1] - N_FRAMES
