@@ -108,6 +108,32 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
                       const uint8_t* suppress_mask, int32_t* tokens, float* sum_logprob, float* no_speech_prob,
                       int32_t* out_len, void* workspace, size_t workspace_bytes, int* steps_run, void* stream);
 
+/* ---- beam search decode (openai-whisper decoding.py::BeamSearchDecoder at temperature 0; replaces the decode inside
+ * whisper_pro_asr.py:433 when the preset sets beam_size, config/components/asr/openai_whisper.py:225-292) -----------------
+ * Rows are windows x beams (row = window * beam_size + beam).  The self-attention cache is never permuted: every row carries the
+ * table of physical cache rows its history lives in (`anc`).  All buffers are device memory owned by the caller:
+ *   tokens       int32 [2][rows][tokens_stride]  both copies pre-filled with the n_initial prompt tokens of every row
+ *   anc          int16 [2][rows][n_text_ctx]     both copies pre-filled with the row index
+ *   sum_logprob  fp32  [2][rows]                 zeroed; after the run the live beams' scores are in copy (steps_run & 1)
+ *   fin_tokens   int32 [n_audio][max_candidates][tokens_stride], fin_score fp32, fin_len int32 (prompt + sampled + EOT),
+ *   fin_count    int32 [n_audio] zeroed, audio_done uint8 [n_audio] zeroed
+ * After the run the live token rows are in copy (steps_run & 1); BeamSearchDecoder.finalize and the MaximumLikelihoodRanker are
+ * host logic on these buffers (whisperjav_b200/model.py).  Workspace: wjb_decode_workspace_bytes(m, rows). */
+typedef struct wjb_beam_bufs {
+    int32_t n_audio, beam_size, max_candidates; /* max_candidates = round(beam_size * patience) */
+    int32_t* tokens;
+    int16_t* anc;
+    float* sum_logprob;
+    int32_t* fin_tokens;
+    float* fin_score;
+    int32_t* fin_len;
+    int32_t* fin_count;
+    uint8_t* audio_done;
+} wjb_beam_bufs;
+int wjb_decode_beam(wjb_model* m, const void* cross_kv, const wjb_beam_bufs* bufs, const wjb_decode_opts* opts,
+                    const uint8_t* suppress_mask, float* no_speech_prob, void* workspace, size_t workspace_bytes, int* steps_run,
+                    void* stream);
+
 /* ---- building blocks exposed for parity tests and profiling ---------------------------------- */
 /* out[r][n] = epilogue(sum_k A[r][k] W[n][k]); flags: 1 = GELU (exact erf).  All fp16, fp32 accumulate. */
 int wjb_gemm_f16(const void* A, int64_t a_row_stride, int64_t a_batch_stride, int rows_per_batch, int n_batch, int K,

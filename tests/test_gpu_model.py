@@ -158,3 +158,41 @@ def test_temperature_fallback_and_sampling(tiny, clips):
     out = m.transcribe_batch(clips[:2], language="ja", temperature=(0.0, 0.5), logprob_threshold=-50.0, no_speech_threshold=None,
                              compression_ratio_threshold=None, condition_on_previous_text=False, max_initial_timestamp=0.0)
     assert all(s_["temperature"] == 0.0 for o in out for s_ in o["segments"])
+
+
+@pytest.mark.parametrize("beam,patience", [(1, None), (2, 1.2), (3, 1.5)])
+def test_beam_search_matches_oracle(tiny, clips, diag_dir, beam, patience):
+    """BeamSearchDecoder on the device (ancestry-table KV cache, per-window candidate ranking) against the oracle's restatement,
+    short horizon so that the oracle finishes in seconds.  Scores of competing hypotheses can be closer than fp16 logit noise, so
+    identity is required for most windows and a close score for all of them; beam_size 1 must reproduce the greedy decode."""
+    dims, w, m = tiny
+    xa = m.encode(_gpu_mel(m, clips))
+    kw = dict(language="ja", without_timestamps=True, sample_len=12)
+    res = m.decode_features(xa, beam_size=beam, patience=patience, **kw)
+    if beam == 1:
+        greedy = m.decode_features(xa, **kw)
+        assert [r.tokens for r in res] == [r.tokens for r in greedy]
+        assert [r.sum_logprob for r in res] == pytest.approx([r.sum_logprob for r in greedy], abs=1e-3)
+        assert [r.no_speech_prob for r in res] == pytest.approx([r.no_speech_prob for r in greedy], abs=1e-6)
+    opts = wo.DecodingOptions(language="ja", without_timestamps=True, sample_len=12, beam_size=beam, patience=patience)
+    ref = wo.decode(w, dims, None, opts, True, audio_features=xa.float().cpu())
+    report = [{"gpu": g.tokens, "oracle": r.tokens, "gpu_sum": g.sum_logprob, "oracle_sum": r.sum_logprob} for g, r in zip(res, ref)]
+    (diag_dir / f"beam_tiny_{beam}.json").write_text(json.dumps(report, indent=1))
+    same = sum(g.tokens == r.tokens for g, r in zip(res, ref))
+    for g, r in zip(res, ref):
+        assert abs(g.no_speech_prob - r.no_speech_prob) <= 1e-3 + 0.02 * r.no_speech_prob
+        assert abs(g.avg_logprob - r.avg_logprob) <= 0.1, report  # a different pick among near-equal hypotheses scores about the same
+        if g.tokens == r.tokens:
+            assert abs(g.sum_logprob - r.sum_logprob) <= 0.15
+    assert same >= len(ref) - 1, report
+    # again: bit-reproducible
+    res2 = m.decode_features(xa, beam_size=beam, patience=patience, **kw)
+    assert [r.tokens for r in res2] == [r.tokens for r in res]
+
+
+def test_transcribe_with_beam_size_runs_the_beam_decoder(tiny, clips):
+    dims, w, m = tiny
+    s0 = m.stats["device_passes"]
+    out = m.transcribe_batch(clips[:2], language="ja", temperature=0.0, beam_size=2, patience=1.2, condition_on_previous_text=False,
+                             without_timestamps=True, sample_len=8)
+    assert len(out) == 2 and all("segments" in o for o in out) and m.stats["device_passes"] > s0

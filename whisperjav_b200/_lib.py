@@ -27,6 +27,13 @@ class DecodeOpts(C.Structure):
         "tokens_stride", "check_every")] + [("temperature", C.c_float), ("seed", C.c_uint32)]
 
 
+class BeamBufs(C.Structure):
+    """include/wjb200.h::wjb_beam_bufs"""
+    _fields_ = [("n_audio", C.c_int32), ("beam_size", C.c_int32), ("max_candidates", C.c_int32), ("tokens", C.c_void_p),
+                ("anc", C.c_void_p), ("sum_logprob", C.c_void_p), ("fin_tokens", C.c_void_p), ("fin_score", C.c_void_p),
+                ("fin_len", C.c_void_p), ("fin_count", C.c_void_p), ("audio_done", C.c_void_p)]
+
+
 _SIGS = {
     "wjb_abi_version": (C.c_int, []),
     "wjb_last_error": (C.c_char_p, []),
@@ -47,6 +54,8 @@ _SIGS = {
     "wjb_decode_greedy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(DecodeOpts), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int),
                                     C.c_void_p]),
+    "wjb_decode_beam": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(BeamBufs), C.POINTER(DecodeOpts), C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_size_t, C.POINTER(C.c_int), C.c_void_p]),
     "wjb_gemm_f16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "wjb_gemm_splitk_workspace_bytes": (C.c_size_t, []),

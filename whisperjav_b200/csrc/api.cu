@@ -509,7 +509,8 @@ size_t wjb_decode_workspace_bytes(const wjb_model* m, int batch) {
 
 // One decoder step for the batch rows [b0, b0 + B) of a run over Btot rows, on stream s.
 static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, int Btot, int b0, int B, int branch, const wjb_decode_opts& o,
-                         const uint8_t* suppress_mask, int32_t* tokens0, float* slp0, float* nsp0, int32_t* out_len0, cudaStream_t s) {
+                         const uint8_t* suppress_mask, int32_t* tokens0, float* slp0, float* nsp0, int32_t* out_len0, cudaStream_t s,
+                         const BeamBufs* beam = nullptr) {
     const wjb_dims& d = m->d;
     const int n = d.n_text_state, H = d.n_text_head, T = d.n_audio_ctx;
     // debugging aid: WJB_DECODE_SKIP bit mask removes kernel classes from the step (1 LN, 2 GEMM, 4 self-attn, 8 cross-attn)
@@ -599,16 +600,22 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
             return launch_gemm_skinny(A, K, W, ldw, bias, res, out, (int)out_stride, B, N, K, flags, s);
         return launch_gemm(q, s);
     };
-    if (int e = launch_embed(tokens, o.tokens_stride, m->h16("dec.emb"), m->h16("dec.pos"), w.x, w.ctl, B, n, s)) return e;
+    // beam search: rows = windows x beams; token rows and the cache ancestry are double buffered by step parity, the rows of a
+    // window share its cross K/V
+    const int kv_div = beam ? beam->beam : 1;
+    if (int e = launch_embed(beam ? beam->tokens : tokens, o.tokens_stride, m->h16("dec.emb"), m->h16("dec.pos"), w.x, w.ctl, B, n, s,
+                             beam ? beam->tokens_parity_stride : 0))
+        return e;
     const size_t self_per_layer = (size_t)Btot * 2 * H * d.n_text_ctx * 64, self_row = (size_t)2 * H * d.n_text_ctx * 64;
-    const size_t cross_per_layer = (size_t)Btot * 2 * H * T * 64, cross_row = (size_t)2 * H * T * 64;
+    const size_t cross_per_layer = (size_t)(Btot / kv_div) * 2 * H * T * 64, cross_row = (size_t)2 * H * T * 64;
     for (int i = 0; i < d.n_text_layer; ++i) {
         const std::string p = "dec." + std::to_string(i) + ".";
         if (int e = linear(w.x, n, m->h16(p + "qkv.w"), n, m->h16(p + "qkv.b"), nullptr, w.qkv, 3 * n, 3 * n, 0, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"))) return e;
-        if (!(skip & 4)) if (int e = launch_attn_dec_self(w.qkv, w.self_kv + i * self_per_layer + b0 * self_row, w.a, &w.ctl->step, w.done, B, H, d.n_text_ctx, s)) return e;
+        if (!(skip & 4)) if (int e = launch_attn_dec_self(w.qkv, w.self_kv + i * self_per_layer + b0 * self_row, w.a, &w.ctl->step, w.done, B, H, d.n_text_ctx, s,
+                                                      beam ? beam->anc : nullptr, beam ? beam->anc_parity_stride : 0)) return e;
         if (int e = linear(w.a, n, m->h16(p + "out.w"), n, m->h16(p + "out.b"), w.x, w.x, n, n, 0)) return e;
         if (int e = linear(w.x, n, m->h16(p + "cq.w"), n, m->h16(p + "cq.b"), nullptr, w.q, n, n, 0, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"))) return e;
-        if (!(skip & 8)) if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv0) + i * cross_per_layer + b0 * cross_row, w.a, w.done, B, H, T, s))
+        if (!(skip & 8)) if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv0) + i * cross_per_layer + b0 * cross_row, w.a, w.done, B, H, T, s, kv_div))
             return e;
         if (int e = linear(w.a, n, m->h16(p + "cout.w"), n, m->h16(p + "cout.b"), w.x, w.x, n, n, 0)) return e;
         if (int e = linear(w.x, n, m->h16(p + "fc1.w"), n, m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, 4 * n, GEMM_GELU, m->h16(p + "ln3.g"), m->h16(p + "ln3.b"))) return e;
@@ -630,6 +637,7 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
     p.max_initial_timestamp_index = o.max_initial_timestamp_index;
     p.n_ctx = d.n_text_ctx;
     p.tokens_stride = o.tokens_stride;
+    if (beam) return launch_beam_select(w.logits, suppress_mask, *beam, nsp, w.done, w.ctl, p, s);
     return launch_sample(w.logits, suppress_mask, tokens, nullptr, slp, nsp, out_len, w.done, w.ctl, p, s);
 }
 
@@ -876,6 +884,114 @@ int wjb_profile_read(float* ms_by_class, int* launches_by_class, int n_classes) 
     }
     g_prof.clear();
     return 0;
+}
+
+// ------------------------------------------------------------------ beam search decode
+int wjb_decode_beam(wjb_model* m, const void* cross_kv, const wjb_beam_bufs* bufs, const wjb_decode_opts* opts, const uint8_t* suppress_mask,
+                    float* no_speech_prob, void* workspace, size_t workspace_bytes, int* steps_run, void* stream) {
+    if (!m || !cross_kv || !bufs || !opts || !no_speech_prob || !workspace) return set_error("decode_beam: null argument");
+    if (!bufs->tokens || !bufs->anc || !bufs->sum_logprob || !bufs->fin_tokens || !bufs->fin_score || !bufs->fin_len || !bufs->fin_count ||
+        !bufs->audio_done)
+        return set_error("decode_beam: null buffer");
+    const wjb_dims& d = m->d;
+    const wjb_decode_opts& o = *opts;
+    const int n_audio = bufs->n_audio, beam = bufs->beam_size, rows = n_audio * beam;
+    if (n_audio < 1 || beam < 1 || beam > kMaxBeam) return set_error("decode_beam: beam_size %d outside 1..%d", beam, kMaxBeam);
+    if (bufs->max_candidates < 1 || bufs->max_candidates > kMaxBeam * 4) return set_error("decode_beam: max_candidates %d", bufs->max_candidates);
+    if (o.temperature != 0.f) return set_error("decode_beam: beam search runs at temperature 0");
+    if (o.n_initial < 1 || o.sample_len < 1) return set_error("decode_beam: bad n_initial/sample_len");
+    const int total_steps = o.n_initial - 1 + o.sample_len;
+    if (total_steps > d.n_text_ctx) return set_error("decode_beam: n_initial + sample_len exceeds n_text_ctx");
+    if (o.tokens_stride < o.n_initial + o.sample_len) return set_error("decode_beam: tokens_stride too small");
+    cudaStream_t s = m->own_stream;
+    cudaEventRecord(m->ev, (cudaStream_t)stream);
+    cudaStreamWaitEvent(s, m->ev, 0);
+    DecWs w = dec_ws(d, rows, reinterpret_cast<uint8_t*>(workspace));
+    if (w.total > workspace_bytes) return set_error("decode_beam: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    BeamBufs bb;
+    bb.n_audio = n_audio;
+    bb.beam = beam;
+    bb.rows = rows;
+    bb.max_candidates = bufs->max_candidates;
+    bb.tokens = bufs->tokens;
+    bb.tokens_parity_stride = (long long)rows * o.tokens_stride;
+    bb.anc = bufs->anc;
+    bb.anc_parity_stride = (long long)rows * d.n_text_ctx;
+    bb.sum_logprob = bufs->sum_logprob;
+    bb.fin_tokens = bufs->fin_tokens;
+    bb.fin_score = bufs->fin_score;
+    bb.fin_len = bufs->fin_len;
+    bb.fin_count = bufs->fin_count;
+    bb.audio_done = bufs->audio_done;
+
+    DecodeCtl h_ctl;
+    h_ctl.step = 0;
+    h_ctl.n_initial = o.n_initial;
+    h_ctl.sot_index = o.sot_index;
+    h_ctl.max_steps = o.sample_len;
+    h_ctl.n_done = 0;
+    h_ctl.temperature = 0.f;
+    h_ctl.seed = 0;
+    cudaError_t ce;
+    if ((ce = cudaMemcpyAsync(w.ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+        return set_error("decode_beam ctl copy: %s", cudaGetErrorString(ce));
+    cudaMemsetAsync(w.done, 0, rows, s);
+    for (int i = 0; i < wjb_model::kMaxSplit; ++i) cudaMemsetAsync(w.splitk + kSplitKSlot * i, 0, kSplitKCounters * sizeof(unsigned), s);
+    cudaMemsetAsync(no_speech_prob, 0, sizeof(float) * n_audio, s);
+    if ((ce = cudaStreamSynchronize(s)) != cudaSuccess) return set_error("decode_beam: setup sync: %s", cudaGetErrorString(ce));
+
+    // one step as a CUDA graph (re-captured per call: its identity would be a dozen pointers and a run is hundreds of replays)
+    const bool use_graph = getenv("WJB_NO_GRAPH") == nullptr;
+    cudaGraphExec_t exec = nullptr;
+    auto one_step = [&]() -> int {
+        if (int e = decode_branch(m, w, cross_kv, rows, 0, rows, 0, o, suppress_mask, nullptr, nullptr, no_speech_prob, nullptr, s, &bb)) return e;
+        return launch_advance(w.ctl, s);
+    };
+    if (use_graph) {
+        cudaGraph_t graph = nullptr;
+        if ((ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
+            return set_error("decode_beam: begin capture: %s", cudaGetErrorString(ce));
+        static const bool want_pdl = getenv("WJB_NO_PDL") == nullptr;
+        set_pdl(want_pdl);
+        int e = one_step();
+        set_pdl(false);
+        ce = cudaStreamEndCapture(s, &graph);
+        if (e) {
+            if (graph) cudaGraphDestroy(graph);
+            return e;
+        }
+        if (ce != cudaSuccess) return set_error("decode_beam: end capture: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return set_error("decode_beam: graph instantiate: %s", cudaGetErrorString(ce));
+    }
+    const int check_every = o.check_every > 0 ? o.check_every : 8;
+    int step = 0, rc = 0;
+    for (; step < total_steps; ++step) {
+        if (use_graph) {
+            if ((ce = cudaGraphLaunch(exec, s)) != cudaSuccess) {
+                rc = set_error("decode_beam: graph launch: %s", cudaGetErrorString(ce));
+                break;
+            }
+        } else if ((rc = one_step()) != 0) {
+            break;
+        }
+        if ((step + 1) % check_every == 0 && step + 1 >= o.n_initial) {
+            cudaMemcpyAsync(m->h_done, &w.ctl->n_done, sizeof(int), cudaMemcpyDeviceToHost, s);
+            if ((ce = cudaStreamSynchronize(s)) != cudaSuccess) {
+                rc = set_error("decode_beam: sync: %s", cudaGetErrorString(ce));
+                break;
+            }
+            if (*m->h_done >= rows) {
+                ++step;
+                break;
+            }
+        }
+    }
+    if (!rc && (ce = cudaStreamSynchronize(s)) != cudaSuccess) rc = set_error("decode_beam: final sync: %s", cudaGetErrorString(ce));
+    if (exec) cudaGraphExecDestroy(exec);
+    if (steps_run) *steps_run = step;
+    return rc;
 }
 
 // ------------------------------------------------------------------ building blocks

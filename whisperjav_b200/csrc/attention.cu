@@ -283,7 +283,8 @@ int launch_attn_encoder(const __half* qkv, __half* out, int B, int T, int H, cud
 constexpr int kSelfThreads = 128;
 __global__ void __launch_bounds__(kSelfThreads) attn_dec_self_kernel(const __half* __restrict__ qkv, __half* __restrict__ kv_cache,
                                                                       __half* __restrict__ out, const int* __restrict__ step_ptr,
-                                                                      const unsigned char* __restrict__ done, int H, int n_ctx) {
+                                                                      const unsigned char* __restrict__ done, int H, int n_ctx,
+                                                                      const short* __restrict__ anc, long long anc_parity_stride) {
     pdl_prologue();
     const int h = blockIdx.x, b = blockIdx.y;
     if (done && done[b]) return;
@@ -292,11 +293,19 @@ __global__ void __launch_bounds__(kSelfThreads) attn_dec_self_kernel(const __hal
     const int T = pos + 1;
     const int n = H * 64;
     __shared__ float sc[448];
+    // beam search: position t of this row's history lives in the cache of physical row src[t] (its ancestor at that step)
+    __shared__ short src[448];
+    if (anc) {
+        const short* arow = anc + (pos & 1) * anc_parity_stride + (long long)b * n_ctx;
+        for (int t = tid; t < pos; t += kSelfThreads) src[t] = arow[t];
+        if (tid == 0) src[pos] = (short)b;
+    }
     __shared__ float red[8];
     __shared__ float osum[4][64];
     const __half* row = qkv + (long long)b * 3 * n;
     uint4* K = reinterpret_cast<uint4*>(kv_cache + ((long long)(b * 2 * H + h) * n_ctx) * 64);
     uint4* V = reinterpret_cast<uint4*>(kv_cache + ((long long)(b * 2 * H + H + h) * n_ctx) * 64);
+    const long long row_pitch = (long long)2 * H * n_ctx * 8;  // uint4 between the caches of consecutive rows
     // append this token's k, v (8 x 16 B each)
     if (tid < 8) K[(long long)pos * 8 + tid] = reinterpret_cast<const uint4*>(row + n + h * 64)[tid];
     if (tid >= 8 && tid < 16) V[(long long)pos * 8 + tid - 8] = reinterpret_cast<const uint4*>(row + 2 * n + h * 64)[tid - 8];
@@ -320,7 +329,8 @@ __global__ void __launch_bounds__(kSelfThreads) attn_dec_self_kernel(const __hal
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int t = t0 + r * 16 + slot;
-            u[r] = (t < T) ? K[(long long)t * 8 + chunk] : make_uint4(0, 0, 0, 0);
+            u[r] = (t < T) ? (anc ? K[((long long)src[t] - b) * row_pitch + (long long)t * 8 + chunk] : K[(long long)t * 8 + chunk])
+                           : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -366,7 +376,8 @@ __global__ void __launch_bounds__(kSelfThreads) attn_dec_self_kernel(const __hal
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int t = t0 + r * 16 + slot;
-            u[r] = (t < T) ? V[(long long)t * 8 + chunk] : make_uint4(0, 0, 0, 0);
+            u[r] = (t < T) ? (anc ? V[((long long)src[t] - b) * row_pitch + (long long)t * 8 + chunk] : V[(long long)t * 8 + chunk])
+                           : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -399,10 +410,10 @@ __global__ void __launch_bounds__(kSelfThreads) attn_dec_self_kernel(const __hal
 }
 
 int launch_attn_dec_self(const __half* qkv, __half* kv_cache, __half* out, const int* step, const unsigned char* done, int B, int H,
-                         int n_ctx, cudaStream_t s) {
+                         int n_ctx, cudaStream_t s, const short* anc, long long anc_parity_stride) {
     if (n_ctx > 448) return set_error("attn_dec_self: n_ctx %d > 448", n_ctx);
     dim3 grid(H, B);
-    launch_k(attn_dec_self_kernel, grid, dim3(kSelfThreads), 0, s, qkv, kv_cache, out, step, done, H, n_ctx);
+    launch_k(attn_dec_self_kernel, grid, dim3(kSelfThreads), 0, s, qkv, kv_cache, out, step, done, H, n_ctx, anc, anc_parity_stride);
     WJB_CHECK_LAUNCH("attn_dec_self");
     return 0;
 }
@@ -414,7 +425,7 @@ constexpr int kCrossMaxT = 1536;
 
 __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
                                                                         __half* __restrict__ out,
-                                                                        const unsigned char* __restrict__ done, int H, int T) {
+                                                                        const unsigned char* __restrict__ done, int H, int T, int kv_div) {
     pdl_prologue();
     const int h = blockIdx.x, b = blockIdx.y;
     if (done && done[b]) return;
@@ -423,8 +434,9 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_kernel(const __h
     __shared__ float sc[kCrossMaxT];
     __shared__ float red[8];
     __shared__ float osum[4][64];
-    const uint4* K = reinterpret_cast<const uint4*>(kv + ((long long)(b * 2 * H + h) * T) * 64);
-    const uint4* V = reinterpret_cast<const uint4*>(kv + ((long long)(b * 2 * H + H + h) * T) * 64);
+    const int bk = b / kv_div;  // beam search: the rows of one window share its K/V
+    const uint4* K = reinterpret_cast<const uint4*>(kv + ((long long)(bk * 2 * H + h) * T) * 64);
+    const uint4* V = reinterpret_cast<const uint4*>(kv + ((long long)(bk * 2 * H + H + h) * T) * 64);
     const int chunk = tid & 7;   // which 16-byte (8 dims) slice of the 64-dim row
     const int slot = tid >> 3;   // key slot 0..15 within an iteration
     float qf[8];
@@ -530,7 +542,7 @@ constexpr int kCbSmem = kCbStages * kCbStageBytes + kCrossMaxT * 4 + 64 * 4 + 4 
 
 __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
                                                                              __half* __restrict__ out,
-                                                                             const unsigned char* __restrict__ done, int H, int T) {
+                                                                             const unsigned char* __restrict__ done, int H, int T, int kv_div) {
     pdl_prologue();
     const int h = blockIdx.x, b = blockIdx.y;
     if (done && done[b]) return;
@@ -542,8 +554,9 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
     uint64_t* full = reinterpret_cast<uint64_t*>(osum + 4 * 64);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = H * 64;
-    const uint8_t* Kg = reinterpret_cast<const uint8_t*>(kv + ((long long)(b * 2 * H + h) * T) * 64);
-    const uint8_t* Vg = reinterpret_cast<const uint8_t*>(kv + ((long long)(b * 2 * H + H + h) * T) * 64);
+    const int bk = b / kv_div;  // beam search: the rows of one window share its K/V
+    const uint8_t* Kg = reinterpret_cast<const uint8_t*>(kv + ((long long)(bk * 2 * H + h) * T) * 64);
+    const uint8_t* Vg = reinterpret_cast<const uint8_t*>(kv + ((long long)(bk * 2 * H + H + h) * T) * 64);
     const int nck = (T + kCbKeys - 1) / kCbKeys;  // chunks per matrix
     const int total = 2 * nck;
     auto chunk_src = [&](int c) { return (c < nck ? Kg : Vg) + (size_t)(c % nck) * kCbStageBytes; };
@@ -656,7 +669,8 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
 }
 
 int launch_attn_dec_cross(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T,
-                          cudaStream_t s) {
+                          cudaStream_t s, int kv_div) {
+    if (kv_div < 1) kv_div = 1;
     if (T > kCrossMaxT) return set_error("attn_dec_cross: T %d > %d", T, kCrossMaxT);
     dim3 grid(H, B);
     static const bool use_bulk = getenv("WJB_CROSS_LSU") == nullptr;
@@ -667,11 +681,11 @@ int launch_attn_dec_cross(const __half* q, const __half* kv, __half* out, const 
             if (e != cudaSuccess) return set_error("cross attr: %s", cudaGetErrorString(e));
             attr = true;
         }
-        cudaError_t e = launch_k(attn_dec_cross_bulk_kernel, grid, dim3(kCrossThreads), (size_t)kCbSmem, s, q, kv, out, done, H, T);
+        cudaError_t e = launch_k(attn_dec_cross_bulk_kernel, grid, dim3(kCrossThreads), (size_t)kCbSmem, s, q, kv, out, done, H, T, kv_div);
         if (e != cudaSuccess) return set_error("attn_dec_cross_bulk launch: %s", cudaGetErrorString(e));
         return 0;
     }
-    launch_k(attn_dec_cross_kernel, grid, dim3(kCrossThreads), 0, s, q, kv, out, done, H, T);
+    launch_k(attn_dec_cross_kernel, grid, dim3(kCrossThreads), 0, s, q, kv, out, done, H, T, kv_div);
     WJB_CHECK_LAUNCH("attn_dec_cross");
     return 0;
 }

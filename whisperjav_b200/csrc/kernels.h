@@ -125,11 +125,13 @@ int launch_logmel(const LogmelArgs& a, cudaStream_t s);
 int launch_attn_encoder(const __half* qkv, __half* out, int B, int T, int H, cudaStream_t s);
 int attn_init();
 // Decoder single-token self-attention with HBM KV cache [B][2H][n_ctx][64] (K heads then V heads).
+// anc (beam search, may be null): [2][B][n_ctx] physical cache row holding each position of a row's history, buffer = step & 1
 int launch_attn_dec_self(const __half* qkv, __half* kv_cache, __half* out, const int* step, const unsigned char* done, int B, int H,
-                         int n_ctx, cudaStream_t s);
+                         int n_ctx, cudaStream_t s, const short* anc = nullptr, long long anc_parity_stride = 0);
 // Decoder single-token cross-attention over kv [B][2H][T][64].
+// kv_div (beam search): row b reads the K/V of window b / kv_div
 int launch_attn_dec_cross(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T,
-                          cudaStream_t s);
+                          cudaStream_t s, int kv_div = 1);
 
 // ---- decoder token logic (decode.cu) -------------------------------------------------------
 struct DecodeCtl {            // device-resident control block, one per decode run
@@ -149,7 +151,24 @@ struct DecodeParams {
     int tokens_stride;        // ints per row in tokens[]
 };
 int launch_embed(const int* tokens, int tokens_stride, const __half* emb, const __half* pos, __half* x, const DecodeCtl* ctl, int B,
-                 int n, cudaStream_t s);
+                 int n, cudaStream_t s, long long parity_stride = 0);
+// beam search state (decode.cu::beam_select_kernel); everything device memory owned by the caller
+constexpr int kMaxBeam = 8;
+struct BeamBufs {
+    int n_audio, beam, rows, max_candidates;
+    int* tokens;                 // [2][rows][tokens_stride], both buffers pre-filled with the initial tokens
+    long long tokens_parity_stride;
+    short* anc;                  // [2][rows][n_ctx] physical cache row of every position, both buffers pre-filled with the row id
+    long long anc_parity_stride;
+    float* sum_logprob;          // [2][rows], zeroed
+    int* fin_tokens;             // [n_audio][max_candidates][tokens_stride]
+    float* fin_score;            // [n_audio][max_candidates]
+    int* fin_len;                // [n_audio][max_candidates] tokens incl. the initial ones and the closing EOT
+    int* fin_count;              // [n_audio], zeroed
+    unsigned char* audio_done;   // [n_audio], zeroed
+};
+int launch_beam_select(const __half* logits, const unsigned char* suppress_mask, const BeamBufs& bb, float* no_speech_prob,
+                       unsigned char* done, DecodeCtl* ctl, const DecodeParams& p, cudaStream_t s);
 int launch_sample(const __half* logits, const unsigned char* suppress_mask, int* tokens, const int* initial_tokens, float* sum_logprob,
                   float* no_speech_prob, int* out_len, unsigned char* done, DecodeCtl* ctl, const DecodeParams& p, cudaStream_t s);
 

@@ -212,9 +212,11 @@ class WhisperB200:
     def decode_features(self, xa: torch.Tensor, *, language="ja", task="transcribe", without_timestamps=False,
                         suppress_tokens="-1", suppress_blank=True, max_initial_timestamp: Optional[float] = 1.0,
                         sample_len: Optional[int] = None, prompt: Optional[Sequence[int]] = None,
-                        prefix: Optional[Sequence[int]] = None, temperature: float = 0.0, seed: int = 0) -> List[DecodingResult]:
-        """Decode B windows (upstream DecodingTask.run with GreedyDecoder: argmax at T == 0, Categorical(logits / T)
-        otherwise) in one device-resident loop."""
+                        prefix: Optional[Sequence[int]] = None, temperature: float = 0.0, seed: int = 0,
+                        beam_size: Optional[int] = None, patience: Optional[float] = None,
+                        length_penalty: Optional[float] = None) -> List[DecodingResult]:
+        """Decode B windows (upstream DecodingTask.run) in one device-resident loop: GreedyDecoder (argmax at T == 0,
+        Categorical(logits / T) otherwise) or, with ``beam_size``, BeamSearchDecoder at T == 0."""
         d = self.dims
         B = xa.shape[0]
         tok = Tokens(d.n_vocab, language, task)
@@ -251,6 +253,10 @@ class WhisperB200:
             mk[tok.suppress_list(suppress_tokens)] = 1
             mask = mk.to(self.device)
             self._bufs[key] = mask
+        if beam_size:
+            if temperature != 0.0:
+                raise ValueError("beam search runs at temperature 0 (upstream drops beam_size when t > 0)")
+            return self._decode_beam(xa, opts, mask, initial, tok, int(beam_size), patience, length_penalty, language)
         with torch.cuda.device(self.device):
             kv_bytes = self.lib.wjb_cross_kv_bytes(self._h, B)
             kv = self._buf("cross_kv", kv_bytes)
@@ -286,6 +292,79 @@ class WhisperB200:
                                           sum_logprob=float(h_slp[b])))
         return results
 
+    def _decode_beam(self, xa, opts, mask, initial, tok, beam: int, patience, length_penalty, language) -> List[DecodingResult]:
+        """upstream decoding.py::DecodingTask.run with BeamSearchDecoder: the device runs update() for every step
+        (``wjb_decode_beam``: rows = windows x beams, cache ancestry tables instead of cache permutation); finalize() and the
+        MaximumLikelihoodRanker are the host logic below, on one device->host read."""
+        d = self.dims
+        n_audio = xa.shape[0]
+        rows = n_audio * beam
+        max_cand = round(beam * (patience or 1.0))
+        if max_cand <= 0:
+            raise ValueError(f"Invalid beam size ({beam}) or patience ({patience})")
+        n_initial, stride, n_ctx = opts.n_initial, opts.tokens_stride, d.n_text_ctx
+        dev = self.device
+        with torch.cuda.device(dev):
+            kv_bytes = self.lib.wjb_cross_kv_bytes(self._h, n_audio)
+            kv = self._buf("cross_kv", kv_bytes)
+            _lib.check(self.lib.wjb_cross_kv(self._h, _lib.ptr(xa), n_audio, _lib.ptr(kv), _lib.stream_ptr()), "wjb_cross_kv")
+            ws_bytes = self.lib.wjb_decode_workspace_bytes(self._h, rows)
+            ws = self._buf("dec_ws", ws_bytes)
+            tokens = torch.zeros(2, rows, stride, dtype=torch.int32, device=dev)
+            tokens[:, :, :n_initial] = torch.tensor(initial, dtype=torch.int32, device=dev)
+            anc = torch.arange(rows, dtype=torch.int16, device=dev).view(1, rows, 1).expand(2, rows, n_ctx).contiguous()
+            slp = torch.zeros(2, rows, dtype=torch.float32, device=dev)
+            fin_tokens = torch.zeros(n_audio, max_cand, stride, dtype=torch.int32, device=dev)
+            fin_score = torch.zeros(n_audio, max_cand, dtype=torch.float32, device=dev)
+            fin_len = torch.zeros(n_audio, max_cand, dtype=torch.int32, device=dev)
+            fin_count = torch.zeros(n_audio, dtype=torch.int32, device=dev)
+            audio_done = torch.zeros(n_audio, dtype=torch.uint8, device=dev)
+            nsp = torch.zeros(n_audio, dtype=torch.float32, device=dev)
+            bufs = _lib.BeamBufs(n_audio, beam, max_cand, _lib.ptr(tokens), _lib.ptr(anc), _lib.ptr(slp), _lib.ptr(fin_tokens),
+                                 _lib.ptr(fin_score), _lib.ptr(fin_len), _lib.ptr(fin_count), _lib.ptr(audio_done))
+            steps = C.c_int(0)
+            _lib.check(self.lib.wjb_decode_beam(self._h, _lib.ptr(kv), C.byref(bufs), C.byref(opts), _lib.ptr(mask), _lib.ptr(nsp),
+                                                _lib.ptr(ws), ws_bytes, C.byref(steps), _lib.stream_ptr()), "wjb_decode_beam")
+            par = steps.value & 1  # live rows after the last executed step
+            h_live = tokens[par].cpu().numpy()
+            h_slp = slp[par].cpu().numpy()
+            h_fin_tok, h_fin_score = fin_tokens.cpu().numpy(), fin_score.cpu().numpy()
+            h_fin_len, h_fin_count = fin_len.cpu().numpy(), fin_count.cpu().numpy()
+            h_nsp = nsp.cpu().numpy()
+        self.stats["decode_steps"] += steps.value
+        self.stats["windows"] += n_audio
+        self.stats["device_passes"] += 1
+        live_len = min(steps.value + 1, stride)  # tokens per live row: the prompt plus one per executed sampling step
+        results = []
+        for a in range(n_audio):
+            # BeamSearchDecoder.finalize: finished sequences first, topped up with the best live beams (+ EOT) if fewer than beam
+            seqs: Dict[tuple, float] = {}
+            for k in range(int(h_fin_count[a])):
+                seqs[tuple(int(t) for t in h_fin_tok[a, k, : int(h_fin_len[a, k])])] = float(h_fin_score[a, k])
+            if len(seqs) < beam:
+                order = list(np.argsort(h_slp[a * beam: (a + 1) * beam]))[::-1]
+                for j in order:
+                    seq = tuple(int(t) for t in h_live[a * beam + j, :live_len]) + (tok.eot,)
+                    seqs[seq] = float(h_slp[a * beam + j])
+                    if len(seqs) >= beam:
+                        break
+            cands = []
+            for seq, score in seqs.items():
+                body = list(seq[n_initial:])
+                body = body[: body.index(tok.eot)] if tok.eot in body else body
+                cands.append((body, score))
+            # MaximumLikelihoodRanker.rank: logprob / length (or the Google NMT penalty)
+            def _norm(c):
+                length = len(c[0])
+                pen = length if length_penalty is None else ((5 + length) / 6) ** length_penalty
+                return c[1] / pen if pen else float("-inf")
+            ids, score = max(cands, key=_norm)
+            text = detokenize([t for t in ids if t < tok.eot]).strip()
+            results.append(DecodingResult(tokens=ids, text=text, avg_logprob=score / (len(ids) + 1), no_speech_prob=float(h_nsp[a]),
+                                          temperature=0.0, compression_ratio=compression_ratio(text) if text else 0.0, language=language,
+                                          sum_logprob=score))
+        return results
+
     # ------------------------------------------------------------------ upstream-shaped API
     def transcribe(self, audio: Union[np.ndarray, torch.Tensor], **params) -> dict:
         """``whisper_model.transcribe(audio, **params)`` (whisper_pro_asr.py:433)."""
@@ -306,11 +385,11 @@ class WhisperB200:
         task = decode_options.pop("task", "transcribe")
         decode_options.pop("fp16", None)
         best_of = decode_options.pop("best_of", None) or 1
-        if decode_options.pop("beam_size", None):
-            import logging
-            logging.getLogger("whisperjav").warning("b200 backend: beam search not built yet; T == 0 passes decode greedily")
-        decode_options.pop("patience", None)
-        decode_options.pop("length_penalty", None)
+        # upstream decode_with_fallback: beam_size / patience apply at t == 0, best_of at t > 0
+        beam_opts = {"beam_size": decode_options.pop("beam_size", None), "patience": decode_options.pop("patience", None),
+                     "length_penalty": decode_options.pop("length_penalty", None)}
+        if beam_opts["beam_size"]:
+            decode_options["_beam"] = beam_opts
         temps = [temperature] if isinstance(temperature, (int, float)) else list(temperature)
         d = self.dims
         tok = Tokens(d.n_vocab, language, task)
@@ -448,7 +527,8 @@ class WhisperB200:
         results: List[Optional[DecodingResult]] = [None] * len(prompts)
         for p, idxs in groups.items():
             sub = xa if len(idxs) == len(prompts) else xa[torch.tensor(idxs, device=self.device)].contiguous()
-            res = self.decode_features(sub, language=language, task=task, prompt=list(p) or None, temperature=temperature, seed=seed,
+            beam_kw = dict(decode_options.get("_beam") or {}) if temperature == 0 else {}
+            res = self.decode_features(sub, language=language, task=task, prompt=list(p) or None, temperature=temperature, seed=seed, **beam_kw,
                                        **{k: v for k, v in decode_options.items() if k in
                                           ("without_timestamps", "suppress_tokens", "suppress_blank", "max_initial_timestamp",
                                            "sample_len", "prefix")})
