@@ -124,3 +124,37 @@ def test_beam_never_scores_below_greedy_prefix_quality(tiny):
         assert math.isfinite(b.avg_logprob) and len(b.tokens) <= 8
         if len(g.tokens) < 8 and g.tokens == b.tokens:
             assert b.sum_logprob == pytest.approx(g.sum_logprob, abs=2e-3)
+
+
+def test_host_finalize_and_ranker_agree_with_the_oracle():
+    """whisperjav_b200.hostlogic.beam_finalize_and_rank (the host half of the device beam search) against the oracle's
+    BeamSearch.finalize + rank_maximum_likelihood on random finished / live sets."""
+    from whisperjav_b200.hostlogic import beam_finalize_and_rank
+
+    rng = np.random.default_rng(5)
+    eot, n_initial = 99, 3
+    for trial in range(200):
+        beam = int(rng.integers(1, 5))
+        T = int(rng.integers(4, 9))
+        n_fin = int(rng.integers(0, beam + 2))
+        prompt = [7, 8, 9]
+        finished = []
+        seen = set()
+        for _ in range(n_fin):
+            L = int(rng.integers(1, T - n_initial + 1))
+            seq = tuple(prompt + [int(x) for x in rng.integers(10, 90, L)] + [eot])
+            if seq in seen:
+                continue
+            seen.add(seq)
+            finished.append((seq, float(-rng.uniform(0.5, 9.0))))
+        live_tok = np.array([prompt + [int(x) for x in rng.integers(10, 90, T - n_initial)] for _ in range(beam)])
+        live_sum = -rng.uniform(0.5, 9.0, beam)
+        lp = None if trial % 3 else float(rng.uniform(0.0, 1.5))
+        ids, score = beam_finalize_and_rank(finished, [(live_tok[j], float(live_sum[j])) for j in range(beam)], beam, n_initial, eot, lp)
+        b = wo.BeamSearch(beam, eot)
+        b.finished_sequences = [dict(finished)]
+        toks, sums = b.finalize(torch.tensor(live_tok)[None], torch.tensor(live_sum, dtype=torch.float64)[None])
+        cand = [[t[n_initial: int((t == eot).nonzero()[0, 0])] for t in s] for s in toks]
+        sel = wo.rank_maximum_likelihood(cand, sums, lp)[0]
+        assert ids == cand[0][sel].tolist(), (trial, finished, live_tok, live_sum)
+        assert score == pytest.approx(sums[0][sel])

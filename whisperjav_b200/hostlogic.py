@@ -370,3 +370,35 @@ def ten_style_segments(flags: Sequence[int], probs: Sequence[float], audio_durat
     r = merge_close_regions(r, min_silence_duration_ms)
     r = pad_regions(r, audio_duration, start_pad_ms, end_pad_ms)
     return split_long_regions(r, max_speech_duration_s)
+
+
+# ----------------------------------------------------------------------------- beam search, host half
+def beam_finalize_and_rank(finished: Sequence[Tuple[Sequence[int], float]], live: Sequence[Tuple[Sequence[int], float]], beam_size: int,
+                           n_initial: int, eot: int, length_penalty: Optional[float] = None) -> Tuple[List[int], float]:
+    """openai-whisper decoding.py::BeamSearchDecoder.finalize + MaximumLikelihoodRanker.rank for one window.
+
+    ``finished``: (token sequence incl. the initial tokens and the closing EOT, sum_logprob) in the order the device collected
+    them; ``live``: the beams still running (token sequence without EOT, sum_logprob).  Fewer than ``beam_size`` finished
+    sequences are topped up with the best live beams, EOT appended.  Returns the sampled tokens (initial tokens and everything
+    from the first EOT on stripped) of the candidate with the best ``sum_logprob / length`` (or the Google-NMT penalty
+    ``((5 + length) / 6) ** length_penalty``) and its sum_logprob."""
+    seqs: Dict[Tuple[int, ...], float] = {}
+    for seq, score in finished:
+        seqs[tuple(int(t) for t in seq)] = float(score)
+    if len(seqs) < beam_size:
+        order = sorted(range(len(live)), key=lambda j: live[j][1])[::-1]  # np.argsort(sum_logprobs)[::-1]
+        for j in order:
+            seqs[tuple(int(t) for t in live[j][0]) + (eot,)] = float(live[j][1])
+            if len(seqs) >= beam_size:
+                break
+    best, best_norm, best_score = None, None, 0.0
+    for seq, score in seqs.items():
+        body = list(seq[n_initial:])
+        if eot in body:
+            body = body[: body.index(eot)]
+        length = len(body)
+        penalty = length if length_penalty is None else ((5 + length) / 6) ** length_penalty
+        norm = score / penalty if penalty else float("-inf")
+        if best_norm is None or norm > best_norm:  # np.argmax: the first maximum wins
+            best, best_norm, best_score = body, norm, score
+    return best if best is not None else [], best_score

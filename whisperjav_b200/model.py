@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .hostlogic import beam_finalize_and_rank
 from .synth import DIMS, Dims, synth_weights
 from .weights import pack_weights
 
@@ -337,28 +338,9 @@ class WhisperB200:
         live_len = min(steps.value + 1, stride)  # tokens per live row: the prompt plus one per executed sampling step
         results = []
         for a in range(n_audio):
-            # BeamSearchDecoder.finalize: finished sequences first, topped up with the best live beams (+ EOT) if fewer than beam
-            seqs: Dict[tuple, float] = {}
-            for k in range(int(h_fin_count[a])):
-                seqs[tuple(int(t) for t in h_fin_tok[a, k, : int(h_fin_len[a, k])])] = float(h_fin_score[a, k])
-            if len(seqs) < beam:
-                order = list(np.argsort(h_slp[a * beam: (a + 1) * beam]))[::-1]
-                for j in order:
-                    seq = tuple(int(t) for t in h_live[a * beam + j, :live_len]) + (tok.eot,)
-                    seqs[seq] = float(h_slp[a * beam + j])
-                    if len(seqs) >= beam:
-                        break
-            cands = []
-            for seq, score in seqs.items():
-                body = list(seq[n_initial:])
-                body = body[: body.index(tok.eot)] if tok.eot in body else body
-                cands.append((body, score))
-            # MaximumLikelihoodRanker.rank: logprob / length (or the Google NMT penalty)
-            def _norm(c):
-                length = len(c[0])
-                pen = length if length_penalty is None else ((5 + length) / 6) ** length_penalty
-                return c[1] / pen if pen else float("-inf")
-            ids, score = max(cands, key=_norm)
+            finished = [(h_fin_tok[a, k, : int(h_fin_len[a, k])], float(h_fin_score[a, k])) for k in range(int(h_fin_count[a]))]
+            live = [(h_live[a * beam + j, :live_len], float(h_slp[a * beam + j])) for j in range(beam)]
+            ids, score = beam_finalize_and_rank(finished, live, beam, n_initial, tok.eot, length_penalty)
             text = detokenize([t for t in ids if t < tok.eot]).strip()
             results.append(DecodingResult(tokens=ids, text=text, avg_logprob=score / (len(ids) + 1), no_speech_prob=float(h_nsp[a]),
                                           temperature=0.0, compression_ratio=compression_ratio(text) if text else 0.0, language=language,
