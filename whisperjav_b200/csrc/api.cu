@@ -91,6 +91,7 @@ static int init_kernels() {
     if (int e = gemm_init()) return e;
     if (int e = gemm_step_init()) return e;
     if (int e = attn_init()) return e;
+    if (int e = attn_cross_init()) return e;
     if (int e = sample_init()) return e;
     done = true;
     return 0;

@@ -538,23 +538,29 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_kernel(const __h
 // completion), so the bytes in flight are not bounded by the LSU's outstanding-request capacity; V chunks are already in
 // flight while the softmax runs.
 constexpr int kCbStages = 4, kCbKeys = 128, kCbStageBytes = kCbKeys * 128;
-constexpr int kCbSmem = kCbStages * kCbStageBytes + kCrossMaxT * 4 + 64 * 4 + 4 * 64 * 4 + 64;
+constexpr int kCbMaxQ = 4;  // queries (beams of one window) that may share one pass over the window's K/V
+constexpr int cb_smem_bytes(int nq) { return kCbStages * kCbStageBytes + nq * kCrossMaxT * 4 + 64 * 4 + 4 * 64 * 4 + 64; }
+constexpr int kCbSmem = cb_smem_bytes(1);
 
+// NQ = 1: one CTA per (row, head); with beam search either the row reads the K/V of window row / kv_div (any beam size), or
+// NQ = beam_size queries of one window share the CTA and the window's K/V stream through shared memory once (blockIdx.y = window).
+template <int NQ>
 __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
                                                                              __half* __restrict__ out,
                                                                              const unsigned char* __restrict__ done, int H, int T, int kv_div) {
     pdl_prologue();
     const int h = blockIdx.x, b = blockIdx.y;
-    if (done && done[b]) return;
+    const int row0 = b * NQ;  // first query row of this CTA
+    if (done && done[row0]) return;  // the beams of a window finish together
     extern __shared__ __align__(128) uint8_t cb_smem[];
     uint8_t* ring = cb_smem;
-    float* sc = reinterpret_cast<float*>(cb_smem + kCbStages * kCbStageBytes);
-    float* red = sc + kCrossMaxT;
+    float* sc = reinterpret_cast<float*>(cb_smem + kCbStages * kCbStageBytes);  // [NQ][kCrossMaxT]
+    float* red = sc + NQ * kCrossMaxT;
     float* osum = red + 64;                      // [4][64]
     uint64_t* full = reinterpret_cast<uint64_t*>(osum + 4 * 64);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = H * 64;
-    const int bk = b / kv_div;  // beam search: the rows of one window share its K/V
+    const int bk = (NQ > 1) ? b : b / kv_div;  // window whose K/V this CTA reads
     const uint8_t* Kg = reinterpret_cast<const uint8_t*>(kv + ((long long)(bk * 2 * H + h) * T) * 64);
     const uint8_t* Vg = reinterpret_cast<const uint8_t*>(kv + ((long long)(bk * 2 * H + H + h) * T) * 64);
     const int nck = (T + kCbKeys - 1) / kCbKeys;  // chunks per matrix
@@ -579,21 +585,26 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
         for (int c = 0; c < kCbStages && c < total; ++c) issue(c);
 
     const int chunk16 = tid & 7, slot = tid >> 3;  // 16 key slots x 8 sixteen-byte pieces
-    float qf[8];
-    {
-        const uint4 u = reinterpret_cast<const uint4*>(q + (long long)b * n + h * 64)[chunk16];
+    float qf[NQ][8];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        const uint4 u = reinterpret_cast<const uint4*>(q + (long long)(row0 + i) * n + h * 64)[chunk16];
         const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 f = __half22float2(h2[j]);
-            qf[2 * j] = f.x;
-            qf[2 * j + 1] = f.y;
+            qf[i][2 * j] = f.x;
+            qf[i][2 * j + 1] = f.y;
         }
     }
-    float acc[8];
+    float acc[NQ][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    float inv = 0.f;
+    for (int i = 0; i < NQ; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float inv[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) inv[i] = 0.f;
     for (int c = 0; c < total; ++c) {
         const int st = c % kCbStages;
         mbar_wait(&full[st], (c / kCbStages) & 1);
@@ -606,85 +617,134 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
                 const int k = it * 16 + slot;
                 const uint4 u = *reinterpret_cast<const uint4*>(base + k * 128 + chunk16 * 16);
                 const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-                float s_ = 0.f;
+                float kf[8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float2 f = __half22float2(h2[j]);
-                    s_ = fmaf(qf[2 * j], f.x, s_);
-                    s_ = fmaf(qf[2 * j + 1], f.y, s_);
+                    kf[2 * j] = f.x;
+                    kf[2 * j + 1] = f.y;
                 }
-                s_ += __shfl_xor_sync(0xffffffffu, s_, 1);
-                s_ += __shfl_xor_sync(0xffffffffu, s_, 2);
-                s_ += __shfl_xor_sync(0xffffffffu, s_, 4);
-                if (chunk16 == 0 && k < keys) sc[key0 + k] = s_ * 0.125f;
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) {
+                    float s_ = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) s_ = fmaf(qf[i][j], kf[j], s_);
+                    s_ += __shfl_xor_sync(0xffffffffu, s_, 1);
+                    s_ += __shfl_xor_sync(0xffffffffu, s_, 2);
+                    s_ += __shfl_xor_sync(0xffffffffu, s_, 4);
+                    if (chunk16 == 0 && k < keys) sc[i * kCrossMaxT + key0 + k] = s_ * 0.125f;
+                }
             }
         } else {
 #pragma unroll
             for (int it = 0; it < kCbKeys / 16; ++it) {
                 const int k = it * 16 + slot;
-                const float w = (k < keys) ? round_f16(sc[key0 + k] * inv) : 0.f;
                 const uint4 u = (k < keys) ? *reinterpret_cast<const uint4*>(base + k * 128 + chunk16 * 16) : make_uint4(0, 0, 0, 0);
                 const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+                float vf[8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float2 f = __half22float2(h2[j]);
-                    acc[2 * j] = fmaf(w, f.x, acc[2 * j]);
-                    acc[2 * j + 1] = fmaf(w, f.y, acc[2 * j + 1]);
+                    vf[2 * j] = f.x;
+                    vf[2 * j + 1] = f.y;
+                }
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) {
+                    const float w = (k < keys) ? round_f16(sc[i * kCrossMaxT + key0 + k] * inv[i]) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(w, vf[j], acc[i][j]);
                 }
             }
         }
         __syncthreads();  // stage consumed by everyone (and, after the last K chunk, all scores are in smem)
         if (tid == 0 && c + kCbStages < total) issue(c + kCbStages);
         if (c == nck - 1) {
-            // softmax over the T scores (V chunks are already streaming into the ring)
-            float mx = -INFINITY;
-            for (int t = tid; t < T; t += kCrossThreads) mx = fmaxf(mx, sc[t]);
-            mx = warp_max(mx);
-            if (lane == 0) red[warp] = mx;
-            __syncthreads();
-            mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-            float sum = 0.f;
-            for (int t = tid; t < T; t += kCrossThreads) {
-                const float e = __expf(sc[t] - mx);
-                sc[t] = e;
-                sum += e;
+            // softmax over the T scores of every query (V chunks are already streaming into the ring)
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                float* sci = sc + i * kCrossMaxT;
+                float mx = -INFINITY;
+                for (int t = tid; t < T; t += kCrossThreads) mx = fmaxf(mx, sci[t]);
+                mx = warp_max(mx);
+                if (i > 0) __syncthreads();  // red[] of the previous query has been read
+                if (lane == 0) red[warp] = mx;
+                __syncthreads();
+                mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+                float sum = 0.f;
+                for (int t = tid; t < T; t += kCrossThreads) {
+                    const float e = __expf(sci[t] - mx);
+                    sci[t] = e;
+                    sum += e;
+                }
+                sum = warp_sum(sum);
+                if (lane == 0) red[4 + warp] = sum;
+                __syncthreads();
+                inv[i] = 1.0f / (red[4] + red[5] + red[6] + red[7]);
             }
-            sum = warp_sum(sum);
-            if (lane == 0) red[4 + warp] = sum;
-            __syncthreads();
-            inv = 1.0f / (red[4] + red[5] + red[6] + red[7]);
         }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
-        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
-    }
-    if (lane < 8) {
+    for (int i = 0; i < NQ; ++i) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) osum[warp * 64 + lane * 8 + j] = acc[j];
+        for (int j = 0; j < 8; ++j) {
+            acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], 8);
+            acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], 16);
+        }
+        if (i > 0) __syncthreads();  // osum of the previous query has been read
+        if (lane < 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) osum[warp * 64 + lane * 8 + j] = acc[i][j];
+        }
+        __syncthreads();
+        if (tid < 64)
+            out[(long long)(row0 + i) * n + h * 64 + tid] = __float2half_rn(osum[tid] + osum[64 + tid] + osum[128 + tid] + osum[192 + tid]);
     }
-    __syncthreads();
-    if (tid < 64) out[(long long)b * n + h * 64 + tid] = __float2half_rn(osum[tid] + osum[64 + tid] + osum[128 + tid] + osum[192 + tid]);
+}
+
+template <int NQ>
+static int launch_cross_bulk(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T, int kv_div,
+                             cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_dec_cross_bulk_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, cb_smem_bytes(NQ));
+        if (e != cudaSuccess) return set_error("cross attr: %s", cudaGetErrorString(e));
+        attr = true;
+    }
+    dim3 grid(H, B / NQ);
+    cudaError_t e = launch_k(attn_dec_cross_bulk_kernel<NQ>, grid, dim3(kCrossThreads), (size_t)cb_smem_bytes(NQ), s, q, kv, out, done, H, T, kv_div);
+    if (e != cudaSuccess) return set_error("attn_dec_cross_bulk launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// set the dynamic shared memory attribute of every instance up front (outside any stream capture)
+int attn_cross_init() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(attn_dec_cross_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cb_smem_bytes(1))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(attn_dec_cross_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cb_smem_bytes(2))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(attn_dec_cross_bulk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cb_smem_bytes(3))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(attn_dec_cross_bulk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cb_smem_bytes(4))) != cudaSuccess)
+        return set_error("cross attr: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 int launch_attn_dec_cross(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T,
                           cudaStream_t s, int kv_div) {
     if (kv_div < 1) kv_div = 1;
     if (T > kCrossMaxT) return set_error("attn_dec_cross: T %d > %d", T, kCrossMaxT);
-    dim3 grid(H, B);
     static const bool use_bulk = getenv("WJB_CROSS_LSU") == nullptr;
     if (use_bulk) {
-        static bool attr = false;
-        if (!attr) {
-            cudaError_t e = cudaFuncSetAttribute(attn_dec_cross_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCbSmem);
-            if (e != cudaSuccess) return set_error("cross attr: %s", cudaGetErrorString(e));
-            attr = true;
+        // beam search: the beams of a window share one pass over its K/V when they fit one CTA
+        static const bool share = !(getenv("WJB_CROSS_SHARE") && atoi(getenv("WJB_CROSS_SHARE")) == 0);
+        if (share && kv_div > 1 && kv_div <= kCbMaxQ && B % kv_div == 0) {
+            switch (kv_div) {
+                case 2: return launch_cross_bulk<2>(q, kv, out, done, B, H, T, kv_div, s);
+                case 3: return launch_cross_bulk<3>(q, kv, out, done, B, H, T, kv_div, s);
+                case 4: return launch_cross_bulk<4>(q, kv, out, done, B, H, T, kv_div, s);
+            }
         }
-        cudaError_t e = launch_k(attn_dec_cross_bulk_kernel, grid, dim3(kCrossThreads), (size_t)kCbSmem, s, q, kv, out, done, H, T, kv_div);
-        if (e != cudaSuccess) return set_error("attn_dec_cross_bulk launch: %s", cudaGetErrorString(e));
-        return 0;
+        return launch_cross_bulk<1>(q, kv, out, done, B, H, T, kv_div, s);
     }
+    dim3 grid(H, B);
     launch_k(attn_dec_cross_kernel, grid, dim3(kCrossThreads), 0, s, q, kv, out, done, H, T, kv_div);
     WJB_CHECK_LAUNCH("attn_dec_cross");
     return 0;

@@ -124,6 +124,7 @@ int launch_logmel(const LogmelArgs& a, cudaStream_t s);
 // Encoder self-attention over qkv [B*T][3n] (q | k | v, heads of 64), out [B*T][n].
 int launch_attn_encoder(const __half* qkv, __half* out, int B, int T, int H, cudaStream_t s);
 int attn_init();
+int attn_cross_init();
 // Decoder single-token self-attention with HBM KV cache [B][2H][n_ctx][64] (K heads then V heads).
 // anc (beam search, may be null): [2][B][n_ctx] physical cache row holding each position of a row's history, buffer = step & 1
 int launch_attn_dec_self(const __half* qkv, __half* kv_cache, __half* out, const int* step, const unsigned char* done, int B, int H,
