@@ -199,9 +199,10 @@ def _gelu(x, r):
     return r(F.gelu(x))  # exact erf GELU (nn.GELU default)
 
 
-def _attention(q, k, v, n_head, causal: bool, r):
+def _attention(q, k, v, n_head, causal: bool, r, capture: Optional[list] = None):
     """model.py::MultiHeadAttention.qkv_attention (SDPA branch: softmax(q k^T / sqrt(d)) v,
-    fp32 softmax, fp16 in/out)."""
+    fp32 softmax, fp16 in/out).  ``capture``: the scaled scores ``qk`` [B, H, Tq, Tk] are appended (what the
+    non-SDPA branch returns next to the output and timing.py collects through forward hooks)."""
     n_batch, n_ctx, n_state = q.shape
     d = n_state // n_head
     q = q.view(n_batch, n_ctx, n_head, d).permute(0, 2, 1, 3)
@@ -212,6 +213,8 @@ def _attention(q, k, v, n_head, causal: bool, r):
         t_k = k.shape[2]
         mask = torch.full((n_ctx, t_k), float("-inf")).triu_(1 + t_k - n_ctx)
         qk = qk + mask
+    if capture is not None:
+        capture.append(qk.float())
     w = r(torch.softmax(qk.float(), dim=-1))  # non-SDPA branch: softmax(qk.float()).to(q.dtype)
     out = w @ v
     return r(out.permute(0, 2, 1, 3).flatten(start_dim=2))
@@ -259,9 +262,11 @@ class DecoderState:
 
 
 def decoder_forward(weights, dims: ModelDimensions, tokens: torch.Tensor, xa: torch.Tensor,
-                    state: Optional[DecoderState] = None, sim_fp16: bool = True) -> torch.Tensor:
+                    state: Optional[DecoderState] = None, sim_fp16: bool = True,
+                    cross_qk: Optional[list] = None) -> torch.Tensor:
     """model.py::TextDecoder.forward with the decoding.py::PyTorchInference KV cache.
-    tokens [B, T] (all tokens on the first call, then the last one) -> fp32 logits [B, T, V]."""
+    tokens [B, T] (all tokens on the first call, then the last one) -> fp32 logits [B, T, V].
+    ``cross_qk``: list that receives every layer's cross-attention scores [B, H, T, n_audio_ctx] (timing.py's hooks)."""
     r = Rounder(sim_fp16)
     if state is None:
         state = DecoderState()
@@ -288,7 +293,7 @@ def decoder_forward(weights, dims: ModelDimensions, tokens: torch.Tensor, xa: to
         if i not in state.cross_k:
             state.cross_k[i] = _linear(xa, weights, p + ".cross_attn.key", r)
             state.cross_v[i] = _linear(xa, weights, p + ".cross_attn.value", r)
-        a = _attention(q, state.cross_k[i], state.cross_v[i], dims.n_text_head, False, r)
+        a = _attention(q, state.cross_k[i], state.cross_v[i], dims.n_text_head, False, r, cross_qk)
         x = r(x + _linear(a, weights, p + ".cross_attn.out", r))
         h = _layer_norm(x, weights, p + ".mlp_ln", r)
         h = _gelu(_linear(h, weights, p + ".mlp.0", r), r)
