@@ -1,0 +1,89 @@
+"""Host half of the temperature ladder (upstream transcribe.py::decode_with_fallback, batched in
+``WhisperB200._decode_with_fallback``) with the device decode replaced by scripted results.  CPU only."""
+import pytest
+import torch
+
+from whisperjav_b200 import model as M
+
+
+def _res(tokens, avg, cr, ns, t):
+    return M.DecodingResult(tokens=list(tokens), text="x" * len(tokens), avg_logprob=avg, no_speech_prob=ns, temperature=t,
+                            compression_ratio=cr, language="ja", sum_logprob=avg * (len(tokens) + 1))
+
+
+class _Scripted(M.WhisperB200):
+    """No device: ``_decode_with_prompts`` pops scripted per-window results and records what it was asked."""
+
+    def __init__(self, script):
+        self.script = script      # {(window id, temperature, draw): DecodingResult}
+        self.calls = []
+        self._sample_calls = 0
+        self.device = "cpu"
+        self.draw = {}
+
+    def _decode_with_prompts(self, xa, prompts, temperature, language, task, decode_options, seed=0):
+        ids = [int(v) for v in xa[:, 0].tolist()]
+        self.calls.append((temperature, ids, seed))
+        out = []
+        for i in ids:
+            k = self.draw.get((i, temperature), 0)
+            self.draw[(i, temperature)] = k + 1
+            out.append(self.script[(i, temperature, k)])
+        return out
+
+
+def _oracle_ladder(script, i, temps, best_of, cr_thr, lp_thr, ns_thr):
+    """decode_with_fallback for one window, best_of candidates ranked by sum_logprob / length at t > 0."""
+    res = None
+    for t in temps:
+        n = best_of if (t > 0 and best_of > 1) else 1
+        cands = [script[(i, t, k)] for k in range(n)]
+        res = max(cands, key=lambda r: r.sum_logprob / max(len(r.tokens), 1)) if n > 1 else cands[0]
+        needs = False
+        if cr_thr is not None and res.compression_ratio > cr_thr:
+            needs = True
+        if lp_thr is not None and res.avg_logprob < lp_thr:
+            needs = True
+        if ns_thr is not None and res.no_speech_prob > ns_thr and lp_thr is not None and res.avg_logprob < lp_thr:
+            needs = False
+        if not needs:
+            break
+    return res
+
+
+@pytest.mark.parametrize("best_of", [1, 3])
+def test_ladder_redecodes_only_the_failing_windows(best_of):
+    temps = [0.0, 0.4, 0.8]
+    good = lambda t: _res([5, 6, 7], -0.3, 1.2, 0.1, t)          # noqa: E731
+    repetitive = lambda t: _res([5] * 9, -0.2, 3.1, 0.1, t)      # noqa: E731  compression ratio too high
+    unsure = lambda t: _res([8, 9], -1.7, 1.1, 0.2, t)           # noqa: E731  avg_logprob too low
+    silent = lambda t: _res([4], -1.9, 1.0, 0.95, t)             # noqa: E731  low logprob but judged silent: accepted
+    script = {}
+    for t in temps:
+        for k in range(3):
+            script[(0, t, k)] = good(t)
+            script[(1, t, k)] = repetitive(t) if t < 0.8 else _res([5, 6, 8, 9][: 2 + k], -0.5 + 0.1 * k, 1.4, 0.1, t)
+            script[(2, t, k)] = unsure(t) if t == 0.0 else _res([8, 9, 10 + k], -0.9 + 0.2 * k, 1.1, 0.2, t)
+            script[(3, t, k)] = silent(t)
+            script[(4, t, k)] = unsure(t)                          # never recovers: the last temperature's result stands
+    m = _Scripted(script)
+    xa = torch.arange(5, dtype=torch.float32).view(5, 1)
+    out = m._decode_with_fallback(xa, [[]] * 5, temps, best_of, "ja", "transcribe", {}, 2.4, -1.0, 0.6)
+    for i in range(5):
+        want = _oracle_ladder(script, i, temps, best_of, 2.4, -1.0, 0.6)
+        assert out[i].tokens == want.tokens and out[i].temperature == want.temperature and out[i].avg_logprob == want.avg_logprob, i
+    # batches shrink: t = 0 sees all windows once, later temperatures only the failing ones, best_of draws each
+    by_t = {}
+    for t, ids, seed in m.calls:
+        by_t.setdefault(t, []).append(ids)
+    assert by_t[0.0] == [[0, 1, 2, 3, 4]]
+    assert by_t[0.4] == [[1, 2, 4]] * best_of
+    assert by_t[0.8] == [[1, 4]] * best_of
+    assert len({seed for _, _, seed in m.calls}) == len(m.calls)   # every sampled pass gets its own seed
+
+
+def test_thresholds_can_be_disabled():
+    script = {(0, 0.0, 0): _res([5] * 9, -3.0, 9.9, 0.0, 0.0), (0, 0.5, 0): _res([1], -0.1, 1.0, 0.0, 0.5)}
+    m = _Scripted(script)
+    out = m._decode_with_fallback(torch.zeros(1, 1), [[]], [0.0, 0.5], 1, "ja", "transcribe", {}, None, None, None)
+    assert out[0].temperature == 0.0 and [c[0] for c in m.calls] == [0.0]
