@@ -108,6 +108,16 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
                       const uint8_t* suppress_mask, int32_t* tokens, float* sum_logprob, float* no_speech_prob,
                       int32_t* out_len, void* workspace, size_t workspace_bytes, int* steps_run, void* stream);
 
+/* Parity-test hook for wjb_decode_greedy (all NULL = off, the production state).  While set, every following greedy run
+ *   - copies the raw fp16 logits of each step to logits_out[step][row][wjb_decode_logits_stride(m)] (upstream: the
+ *     `logits = self.inference.logits(tokens, audio_features)` line of DecodingTask._main_loop, before the logit filters);
+ *     logits_out_bytes must cover (n_initial - 1 + sample_len) steps;
+ *   - records the id the device picked at position p of row b in sampled_out[b][tokens_stride] (p >= n_initial);
+ *   - feeds forced_tokens[b][p] instead of the picked id (teacher forcing; same layout as `tokens`).
+ * The step graph is re-captured when the hook changes; nothing is read from these pointers after a run returns. */
+int wjb_decode_logits_stride(const wjb_model* m);
+int wjb_decode_set_trace(wjb_model* m, void* logits_out, size_t logits_out_bytes, int32_t* sampled_out, const int32_t* forced_tokens);
+
 /* ---- beam search decode (openai-whisper decoding.py::BeamSearchDecoder at temperature 0; replaces the decode inside
  * whisper_pro_asr.py:433 when the preset sets beam_size, config/components/asr/openai_whisper.py:225-292) -----------------
  * Rows are windows x beams (row = window * beam_size + beam).  The self-attention cache is never permuted: every row carries the
@@ -164,9 +174,6 @@ int wjb_gemm_step_ln_f16(const void* A, int64_t a_row_stride, int rows, int K, c
 void wjb_debug_gemm_trace(void* buf);
 /* debugging aid: launch the building blocks below with the programmatic-dependent-launch attribute, as the decode graph does */
 void wjb_debug_set_pdl(int on);
-/* tuning hook for the decode-step GEMM: columns per CTA = 8*nt (nt 1|2|4), ks = K slices per column group (cluster size);
- * 0 = built-in heuristic */
-void wjb_gemm_skinny_config(int nt, int ks);
 int wjb_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int n, void* stream);
 int wjb_attention_encoder_f16(const void* qkv, void* out, int batch, int T, int n_head, void* stream);
 /* single decoder step pieces */

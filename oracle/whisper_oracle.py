@@ -397,8 +397,11 @@ class DecodingResult:
     compression_ratio: float = np.nan
     language: str = "ja"
     sum_logprob: float = np.nan
-    # diagnostics (not in upstream): per-step top-2 logit margin after filtering
+    # diagnostics (not in upstream): per-step top-2 logit margin after filtering; under teacher forcing also the oracle's own
+    # pick per step and how far below the oracle's top filtered logit the forced token sits (0 = the oracle agrees)
     margins: List[float] = field(default_factory=list)
+    picks: List[int] = field(default_factory=list)
+    forced_gap: List[float] = field(default_factory=list)
 
 
 def get_suppress_tokens(tok: SpecialTokens, options: DecodingOptions) -> Tuple[int, ...]:
@@ -478,10 +481,13 @@ def apply_logit_filters(logits: torch.Tensor, tokens: torch.Tensor, tok: Special
 
 def decode(weights, dims: ModelDimensions, mel: torch.Tensor, options: DecodingOptions,
            sim_fp16: bool = True, audio_features: Optional[torch.Tensor] = None,
-           return_logits: bool = False) -> List[DecodingResult]:
+           return_logits: bool = False, forced_tokens: Optional[Sequence[Sequence[int]]] = None) -> List[DecodingResult]:
     """decoding.py::DecodingTask.run for greedy decoding (``beam_size is None``, T == 0).
 
-    mel [B, n_mels, 3000] (or pre-computed ``audio_features`` [B, 1500, n_state])."""
+    mel [B, n_mels, 3000] (or pre-computed ``audio_features`` [B, 1500, n_state]).
+    ``forced_tokens`` (diagnostic, not upstream): per row the sampled ids to feed instead of the oracle's own picks
+    (teacher forcing; a row is fed EOT once its list is exhausted).  ``picks`` / ``forced_gap`` then say, per step, what
+    the oracle would have chosen on that prefix and how far below its top filtered logit the forced id sits."""
     if options.beam_size is not None:
         if return_logits:
             raise NotImplementedError("return_logits is a greedy-path diagnostic")
@@ -510,6 +516,8 @@ def decode(weights, dims: ModelDimensions, mel: torch.Tensor, options: DecodingO
     no_speech_probs = [np.nan] * n_audio
     state = DecoderState()
     margins: List[List[float]] = [[] for _ in range(n_audio)]
+    picks: List[List[int]] = [[] for _ in range(n_audio)]
+    forced_gap: List[List[float]] = [[] for _ in range(n_audio)]
     all_logits = []
     for i in range(sample_len):
         inp = tokens if i == 0 else tokens[:, -1:]
@@ -527,6 +535,14 @@ def decode(weights, dims: ModelDimensions, mel: torch.Tensor, options: DecodingO
         logprobs = F.log_softmax(logits.float(), dim=-1)
         current_logprobs = logprobs[torch.arange(n_audio), next_tokens]
         alive = tokens[:, -1] != tok.eot
+        if forced_tokens is not None:
+            forced = torch.tensor([(list(f)[i] if i < len(f) else tok.eot) for f in forced_tokens])
+            for b in range(n_audio):
+                if alive[b]:
+                    picks[b].append(int(next_tokens[b]))
+                    forced_gap[b].append(float(top2[b, 0] - logits[b, forced[b]]))
+            next_tokens = forced
+            current_logprobs = logprobs[torch.arange(n_audio), next_tokens]
         for b in range(n_audio):
             if alive[b]:
                 margins[b].append(float(top2[b, 0] - top2[b, 1]))
@@ -547,7 +563,8 @@ def decode(weights, dims: ModelDimensions, mel: torch.Tensor, options: DecodingO
         results.append(DecodingResult(tokens=out, text=text, avg_logprob=slp / (len(out) + 1),
                                       no_speech_prob=float(no_speech_probs[b]), temperature=options.temperature,
                                       compression_ratio=compression_ratio(text) if text else 0.0,
-                                      language=options.language or "en", sum_logprob=slp, margins=margins[b]))
+                                      language=options.language or "en", sum_logprob=slp, margins=margins[b],
+                                      picks=picks[b], forced_gap=forced_gap[b]))
     if return_logits:
         return results, all_logits
     return results

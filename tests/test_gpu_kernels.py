@@ -180,34 +180,6 @@ def test_gemm_step_fused_layernorm(lib, M, N, K, bn, S):
     assert torch.equal(A, a_before)  # the residual stream itself is not touched
 
 
-@pytest.mark.parametrize("M,N,K", [(64, 1280, 1280), (64, 3840, 1280), (64, 1280, 5120), (1, 384, 384), (7, 51866, 384), (33, 5120, 1280)])
-def test_gemm_skinny_decode(lib, M, N, K):
-    """Weight-streaming GEMM used by the decoder steps (block_n = -1), all epilogues."""
-    g = torch.Generator().manual_seed(M + N + K)
-    A = (torch.randn(M, K, generator=g)).half().to(DEV)
-    W = (torch.randn(N, K, generator=g) * 0.03).half().to(DEV)
-    bias = (torch.randn(N, generator=g) * 0.3).half().to(DEV)
-    res = (torch.randn(M, N, generator=g)).half().to(DEV)
-    ld = (N + 63) // 64 * 64
-    lin = r16(A.float() @ W.float().t() + bias.float())
-    for flags, use_res in ((0, False), (1, False), (0, True)):
-        out = torch.zeros(M, ld, dtype=torch.float16, device=DEV)
-        rbuf = None
-        if use_res:
-            out[:, :N] = res
-            rbuf = out  # in place, as the decoder uses it
-        _lib.check(lib.wjb_gemm_f16(_lib.ptr(A), K, 0, M, 1, K, _lib.ptr(W), N, K, _lib.ptr(bias), _lib.ptr(rbuf), _lib.ptr(out), ld, 0, flags, -1,
-                                    _lib.stream_ptr()), "skinny")
-        torch.cuda.synchronize()
-        ref = lin
-        if flags:
-            ref = r16(torch.nn.functional.gelu(lin))
-        if use_res:
-            ref = r16(lin + res.float())
-        assert (out[:, :N].float() - ref).abs().max().item() <= 8e-3
-        assert out[:, N:].abs().max().item() == 0 if ld > N else True
-
-
 @pytest.mark.parametrize("C_,stride,T_out", [(128, 1, 3000), (80, 1, 3000), (384, 2, 1500), (1280, 2, 1500)])
 def test_gemm_conv_im2col_free(lib, C_, stride, T_out):
     """k=3 convolution as a GEMM over overlapping rows of the channels-last padded input."""

@@ -54,6 +54,8 @@ _SIGS = {
     "wjb_decode_greedy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(DecodeOpts), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int),
                                     C.c_void_p]),
+    "wjb_decode_logits_stride": (C.c_int, [C.c_void_p]),
+    "wjb_decode_set_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "wjb_decode_beam": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(BeamBufs), C.POINTER(DecodeOpts), C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_size_t, C.POINTER(C.c_int), C.c_void_p]),
     "wjb_gemm_f16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
@@ -67,7 +69,6 @@ _SIGS = {
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "wjb_debug_gemm_trace": (None, [C.c_void_p]),
     "wjb_debug_set_pdl": (None, [C.c_int]),
-    "wjb_gemm_skinny_config": (None, [C.c_int, C.c_int]),
     "wjb_layernorm_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "wjb_attention_encoder_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "wjb_attention_self_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),

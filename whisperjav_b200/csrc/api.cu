@@ -85,15 +85,24 @@ struct ProfScope {
     }
 };
 
-static int init_kernels() {
-    static bool done = false;
-    if (done) return 0;
+int logmel_init();
+int vad_init();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: run the kernel set-up once for every device a caller uses
+// (a process may hold one model per GPU).  Called at the top of every compute entry point, outside any stream capture.
+int ensure_init() {
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_error("no CUDA device");
+    if (dev < 64 && (done_mask >> dev) & 1ull) return 0;
     if (int e = gemm_init()) return e;
     if (int e = gemm_step_init()) return e;
     if (int e = attn_init()) return e;
     if (int e = attn_cross_init()) return e;
     if (int e = sample_init()) return e;
-    done = true;
+    if (int e = logmel_init()) return e;
+    if (int e = vad_init()) return e;
+    if (dev < 64) done_mask |= 1ull << dev;
     return 0;
 }
 
@@ -194,12 +203,15 @@ struct wjb_model {
     float* g_nsp = nullptr;
     int32_t* g_len = nullptr;
     int* h_done = nullptr;  // pinned
+    DecodeCtl* h_ctl = nullptr;  // pinned staging copy of the control block
     cudaStream_t own_stream = nullptr;  // decode runs here (the caller's stream may be the legacy stream, which cannot be captured)
     cudaEvent_t ev = nullptr;
-    static constexpr int kMaxSplit = 8;
-    cudaStream_t br_stream[kMaxSplit] = {};   // decode branches (batch slices) run concurrently inside the step graph
-    cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit] = {};
-    int g_split = 0;
+    // test / diagnostic hook (wjb_decode_set_trace): raw logits of every step, sampled ids, teacher-forced ids
+    __half* trace_logits = nullptr;
+    size_t trace_logits_bytes = 0;
+    int32_t* trace_sampled = nullptr;
+    const int32_t* trace_forced = nullptr;
+    const void *g_trace_logits = nullptr, *g_trace_sampled = nullptr, *g_trace_forced = nullptr;
     const __half* h16(const std::string& name) const { return reinterpret_cast<const __half*>(blob + L.off(name)); }
     const float* f32(const std::string& name) const { return reinterpret_cast<const float*>(blob + L.off(name)); }
 };
@@ -241,24 +253,20 @@ int wjb_weight_info(const wjb_dims* dims, int index, char* name_buf, int name_bu
 int wjb_model_create(const wjb_dims* dims, const void* weights_blob, wjb_model** out) {
     if (!dims_ok(dims)) return set_error("unsupported dims (need head dim 64, n_mels<=128, ctx<=448/1536)");
     if (!weights_blob || !out) return set_error("null argument");
-    if (int e = init_kernels()) return e;
+    if (int e = ensure_init()) return e;
     wjb_model* m = new wjb_model();
     m->d = *dims;
     m->blob = reinterpret_cast<const uint8_t*>(weights_blob);
     m->L = build_layout(*dims);
-    if (cudaHostAlloc(&m->h_done, sizeof(int) * 4, cudaHostAllocDefault) != cudaSuccess) {
-        delete m;
+    if (cudaHostAlloc(&m->h_done, sizeof(int) * 4, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc(&m->h_ctl, sizeof(DecodeCtl), cudaHostAllocDefault) != cudaSuccess) {
+        wjb_model_destroy(m);
         return set_error("cudaHostAlloc failed");
     }
     if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ev, cudaEventDisableTiming) != cudaSuccess) {
-        delete m;
+        wjb_model_destroy(m);
         return set_error("stream/event creation failed");
-    }
-    cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming);
-    for (int i = 0; i < wjb_model::kMaxSplit; ++i) {
-        cudaStreamCreateWithFlags(&m->br_stream[i], cudaStreamNonBlocking);
-        cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming);
     }
     *out = m;
     return 0;
@@ -268,13 +276,9 @@ void wjb_model_destroy(wjb_model* m) {
     if (!m) return;
     if (m->graph) cudaGraphExecDestroy(m->graph);
     if (m->h_done) cudaFreeHost(m->h_done);
+    if (m->h_ctl) cudaFreeHost(m->h_ctl);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->ev) cudaEventDestroy(m->ev);
-    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
-    for (int i = 0; i < wjb_model::kMaxSplit; ++i) {
-        if (m->br_stream[i]) cudaStreamDestroy(m->br_stream[i]);
-        if (m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
-    }
     delete m;
 }
 
@@ -285,6 +289,7 @@ int wjb_logmel_f16(const float* audio, int64_t audio_stride, const int32_t* n_sa
                    void* out, int time_major, int64_t out_clip_stride, int row0, int n_frames, int reflect_total, void* workspace,
                    void* stream) {
     if (!audio || !n_samples || !filters || !out || !workspace) return set_error("logmel: null argument");
+    if (int e = ensure_init()) return e;
     LogmelArgs a;
     a.audio = audio;
     a.audio_stride = audio_stride;
@@ -335,6 +340,7 @@ size_t wjb_encoder_workspace_bytes(const wjb_model* m, int batch) {
 
 int wjb_encoder_forward(wjb_model* m, const void* mel_tm, int batch, void* out, void* workspace, size_t workspace_bytes, void* stream) {
     if (!m || !mel_tm || !out || !workspace) return set_error("encoder: null argument");
+    if (int e = ensure_init()) return e;
     const wjb_dims& d = m->d;
     cudaStream_t s = (cudaStream_t)stream;
     const int B = batch, n = d.n_audio_state, T = d.n_audio_ctx, T2 = 2 * T + 2, C = d.n_mels, H = d.n_audio_head;
@@ -435,6 +441,7 @@ size_t wjb_cross_kv_bytes(const wjb_model* m, int batch) {
 
 int wjb_cross_kv(wjb_model* m, const void* enc_out, int batch, void* kv_out, void* stream) {
     if (!m || !enc_out || !kv_out) return set_error("cross_kv: null argument");
+    if (int e = ensure_init()) return e;
     const wjb_dims& d = m->d;
     if (d.n_audio_state != d.n_text_state) return set_error("cross_kv: audio/text widths differ");
     const int n = d.n_text_state, T = d.n_audio_ctx, H = d.n_text_head;
@@ -466,15 +473,9 @@ struct DecWs {
     __half *x, *h, *qkv, *q, *a, *mlp, *logits, *self_kv;
     DecodeCtl* ctl;
     unsigned char* done;
-    MegaLayer* mega_layers;
-    unsigned* mega_bar;
-    unsigned long long* mega_prof;
-    uint8_t* splitk;  // per decode branch: kSplitKCounters counters, then kSplitKBytes of fp32 partial tiles
     int logits_stride;
     size_t total;
 };
-constexpr size_t kSplitKBytes = 8u << 20;
-constexpr size_t kSplitKSlot = kSplitKCounters * sizeof(unsigned) + kSplitKBytes;
 static DecWs dec_ws(const wjb_dims& d, int B, uint8_t* base) {
     DecWs w;
     const size_t n = d.n_text_state;
@@ -495,10 +496,6 @@ static DecWs dec_ws(const wjb_dims& d, int B, uint8_t* base) {
     w.self_kv = (__half*)take((size_t)d.n_text_layer * B * 2 * d.n_text_head * d.n_text_ctx * 64 * 2);
     w.ctl = (DecodeCtl*)take(sizeof(DecodeCtl));
     w.done = (unsigned char*)take((size_t)B);
-    w.mega_layers = (MegaLayer*)take(sizeof(MegaLayer) * d.n_text_layer);
-    w.mega_bar = (unsigned*)take(256);
-    w.mega_prof = (unsigned long long*)take(8 * 1024);
-    w.splitk = take(kSplitKSlot * wjb_model::kMaxSplit);
     w.total = off;
     return w;
 }
@@ -508,33 +505,46 @@ size_t wjb_decode_workspace_bytes(const wjb_model* m, int batch) {
     return dec_ws(m->d, batch, nullptr).total;
 }
 
-// One decoder step for the batch rows [b0, b0 + B) of a run over Btot rows, on stream s.
-static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, int Btot, int b0, int B, int branch, const wjb_decode_opts& o,
-                         const uint8_t* suppress_mask, int32_t* tokens0, float* slp0, float* nsp0, int32_t* out_len0, cudaStream_t s,
-                         const BeamBufs* beam = nullptr) {
+int wjb_decode_logits_stride(const wjb_model* m) { return m ? ((m->d.n_vocab + 63) & ~63) : 0; }
+
+int wjb_decode_set_trace(wjb_model* m, void* logits_out, size_t logits_out_bytes, int32_t* sampled_out, const int32_t* forced_tokens) {
+    if (!m) return set_error("decode_set_trace: null model");
+    m->trace_logits = reinterpret_cast<__half*>(logits_out);
+    m->trace_logits_bytes = logits_out ? logits_out_bytes : 0;
+    m->trace_sampled = sampled_out;
+    m->trace_forced = forced_tokens;
+    return 0;
+}
+
+// The kernels of one decoder step for B rows on stream s (captured into the step graph).
+static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B, const wjb_decode_opts& o, const uint8_t* suppress_mask,
+                       int32_t* tokens, float* slp, float* nsp, int32_t* out_len, cudaStream_t s, const BeamBufs* beam = nullptr) {
     const wjb_dims& d = m->d;
     const int n = d.n_text_state, H = d.n_text_head, T = d.n_audio_ctx;
-    // debugging aid: WJB_DECODE_SKIP bit mask removes kernel classes from the step (1 LN, 2 GEMM, 4 self-attn, 8 cross-attn)
-    static const int skip = getenv("WJB_DECODE_SKIP") ? atoi(getenv("WJB_DECODE_SKIP")) : 0;
-    DecWs w = w0;  // row-offset views of the shared workspace
-    w.x += (size_t)b0 * n;
-    w.h += (size_t)b0 * n;
-    w.qkv += (size_t)b0 * 3 * n;
-    w.q += (size_t)b0 * n;
-    w.a += (size_t)b0 * n;
-    w.mlp += (size_t)b0 * 4 * n;
-    w.logits += (size_t)b0 * w.logits_stride;
-    w.done += b0;
-    int32_t* tokens = tokens0 + (size_t)b0 * o.tokens_stride;
-    float* slp = slp0 + b0;
-    float* nsp = nsp0 + b0;
-    int32_t* out_len = out_len0 + b0;
-    // LayerNorm (ln_g/ln_b, may be null) followed by the Linear.  The step kernel can run the LayerNorm itself (one launch less,
-    // parity-tested), but its two cluster-wide exchanges cost more than the launch they save: 5.94 vs 5.58 ms/step measured,
-    // so the fusion is opt-in (WJB_DECODE_FUSE_LN=1)
-    static const bool fuse_ln = getenv("WJB_DECODE_FUSE_LN") && atoi(getenv("WJB_DECODE_FUSE_LN")) != 0;
+    // LayerNorm (ln_g / ln_b, may be null) into w.h, then the Linear
     auto linear = [&](const __half* A, int K, const __half* W, int ldw, const __half* bias, const __half* res, __half* out, int N,
                       long long out_stride, int flags, const __half* ln_g = nullptr, const __half* ln_b = nullptr) {
+        if (ln_g) {
+            if (int e = launch_layernorm(A, ln_g, ln_b, w.h, B, K, s)) return e;
+            A = w.h;
+        }
+        if (gemm_step_supported(B, N, K)) {  // the cluster split-K kernel written for exactly this shape class (gemm_step.cu)
+            StepGemmArgs g;
+            g.A = A;
+            g.a_row_stride = K;
+            g.rows = B;
+            g.K = K;
+            g.W = W;
+            g.N = N;
+            g.ldw = ldw;
+            g.bias = bias;
+            g.residual = res;
+            g.out = out;
+            g.out_row_stride = out_stride;
+            g.flags = flags;
+            g.w_constant = true;
+            return launch_gemm_step(g, s);
+        }
         GemmArgs q;
         q.A = A;
         q.a_row_stride = K;
@@ -550,55 +560,6 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
         q.out_row_stride = out_stride;
         q.flags = flags;
         q.block_n = 0;  // auto: 32-wide tiles when that still leaves SMs idle, else 64
-        // a step GEMM has 20-80 output tiles.  Slicing K over more CTAs pays only for the long-K one (fc2: 26 -> 16 us in the
-        // step graph); for K = n_state the meet-in-L2 costs more than the shorter k loop saves (scripts/gemm_graph_probe.py)
-        static const int splitk = getenv("WJB_DECODE_SPLITK") ? atoi(getenv("WJB_DECODE_SPLITK")) : 3;
-        static const int splitk_bn = getenv("WJB_DECODE_SPLITK_BN") ? atoi(getenv("WJB_DECODE_SPLITK_BN")) : 32;
-        static const int splitk_min_k = getenv("WJB_DECODE_SPLITK_MINK") ? atoi(getenv("WJB_DECODE_SPLITK_MINK")) : 4096;
-        if (splitk != 0 && N % 64 == 0 && K >= splitk_min_k) {
-            q.splits = splitk;
-            q.block_n = splitk_bn;
-            q.splitk_cnt = reinterpret_cast<unsigned*>(w.splitk + kSplitKSlot * branch);
-            q.splitk_ws = reinterpret_cast<float*>(w.splitk + kSplitKSlot * branch + kSplitKCounters * sizeof(unsigned));
-            q.splitk_ws_bytes = kSplitKBytes;
-        }
-        if (skip & 2) return 0;
-        // default: the cluster split-K kernel written for exactly this shape class (gemm_step.cu)
-        static const bool use_step = !(getenv("WJB_DECODE_STEPGEMM") && atoi(getenv("WJB_DECODE_STEPGEMM")) == 0);
-        if (use_step && gemm_step_supported(B, N, K)) {
-            StepGemmArgs g;
-            g.A = A;
-            g.a_row_stride = K;
-            g.rows = B;
-            g.K = K;
-            g.W = W;
-            g.N = N;
-            g.ldw = ldw;
-            g.bias = bias;
-            g.residual = res;
-            g.out = out;
-            g.out_row_stride = out_stride;
-            g.flags = flags;
-            g.w_constant = true;
-            if (ln_g && fuse_ln) {
-                g.ln_gamma = ln_g;
-                g.ln_beta = ln_b;
-                return launch_gemm_step(g, s);
-            }
-            if (ln_g) {  // LayerNorm as its own launch into w.h, then the Linear on it
-                if (!(skip & 1)) if (int e = launch_layernorm(A, ln_g, ln_b, w.h, B, K, s)) return e;
-                g.A = w.h;
-            }
-            return launch_gemm_step(g, s);
-        }
-        if (ln_g) {
-            if (!(skip & 1)) if (int e = launch_layernorm(A, ln_g, ln_b, w.h, B, K, s)) return e;
-            q.A = w.h;
-            A = w.h;
-        }
-        static const bool use_skinny = getenv("WJB_DECODE_SKINNY") != nullptr;
-        if (use_skinny && B <= 64 && K % 32 == 0)
-            return launch_gemm_skinny(A, K, W, ldw, bias, res, out, (int)out_stride, B, N, K, flags, s);
         return launch_gemm(q, s);
     };
     // beam search: rows = windows x beams; token rows and the cache ancestry are double buffered by step parity, the rows of a
@@ -607,23 +568,22 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
     if (int e = launch_embed(beam ? beam->tokens : tokens, o.tokens_stride, m->h16("dec.emb"), m->h16("dec.pos"), w.x, w.ctl, B, n, s,
                              beam ? beam->tokens_parity_stride : 0))
         return e;
-    const size_t self_per_layer = (size_t)Btot * 2 * H * d.n_text_ctx * 64, self_row = (size_t)2 * H * d.n_text_ctx * 64;
-    const size_t cross_per_layer = (size_t)(Btot / kv_div) * 2 * H * T * 64, cross_row = (size_t)2 * H * T * 64;
+    const size_t self_per_layer = (size_t)B * 2 * H * d.n_text_ctx * 64;
+    const size_t cross_per_layer = (size_t)(B / kv_div) * 2 * H * T * 64;
     for (int i = 0; i < d.n_text_layer; ++i) {
         const std::string p = "dec." + std::to_string(i) + ".";
         if (int e = linear(w.x, n, m->h16(p + "qkv.w"), n, m->h16(p + "qkv.b"), nullptr, w.qkv, 3 * n, 3 * n, 0, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"))) return e;
-        if (!(skip & 4)) if (int e = launch_attn_dec_self(w.qkv, w.self_kv + i * self_per_layer + b0 * self_row, w.a, &w.ctl->step, w.done, B, H, d.n_text_ctx, s,
-                                                      beam ? beam->anc : nullptr, beam ? beam->anc_parity_stride : 0)) return e;
+        if (int e = launch_attn_dec_self(w.qkv, w.self_kv + i * self_per_layer, w.a, &w.ctl->step, w.done, B, H, d.n_text_ctx, s,
+                                         beam ? beam->anc : nullptr, beam ? beam->anc_parity_stride : 0)) return e;
         if (int e = linear(w.a, n, m->h16(p + "out.w"), n, m->h16(p + "out.b"), w.x, w.x, n, n, 0)) return e;
         if (int e = linear(w.x, n, m->h16(p + "cq.w"), n, m->h16(p + "cq.b"), nullptr, w.q, n, n, 0, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"))) return e;
-        if (!(skip & 8)) if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv0) + i * cross_per_layer + b0 * cross_row, w.a, w.done, B, H, T, s, kv_div))
+        if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv) + i * cross_per_layer, w.a, w.done, B, H, T, s, kv_div))
             return e;
         if (int e = linear(w.a, n, m->h16(p + "cout.w"), n, m->h16(p + "cout.b"), w.x, w.x, n, n, 0)) return e;
         if (int e = linear(w.x, n, m->h16(p + "fc1.w"), n, m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, 4 * n, GEMM_GELU, m->h16(p + "ln3.g"), m->h16(p + "ln3.b"))) return e;
         if (int e = linear(w.mlp, 4 * n, m->h16(p + "fc2.w"), 4 * n, m->h16(p + "fc2.b"), w.x, w.x, n, n, 0)) return e;
     }
-    if (!(skip & 1)) if (int e = launch_layernorm(w.x, m->h16("dec.ln.g"), m->h16("dec.ln.b"), w.h, B, n, s)) return e;
-    if (int e = linear(w.h, n, m->h16("dec.emb"), n, nullptr, nullptr, w.logits, d.n_vocab, w.logits_stride, 0)) return e;
+    if (int e = linear(w.x, n, m->h16("dec.emb"), n, nullptr, nullptr, w.logits, d.n_vocab, w.logits_stride, 0, m->h16("dec.ln.g"), m->h16("dec.ln.b"))) return e;
     DecodeParams p;
     p.B = B;
     p.n_vocab = d.n_vocab;
@@ -638,84 +598,14 @@ static int decode_branch(wjb_model* m, const DecWs& w0, const void* cross_kv0, i
     p.max_initial_timestamp_index = o.max_initial_timestamp_index;
     p.n_ctx = d.n_text_ctx;
     p.tokens_stride = o.tokens_stride;
-    if (beam) return launch_beam_select(w.logits, suppress_mask, *beam, nsp, w.done, w.ctl, p, s);
-    return launch_sample(w.logits, suppress_mask, tokens, nullptr, slp, nsp, out_len, w.done, w.ctl, p, s);
-}
-
-// Fork the step into `split` batch slices on their own streams (captured as parallel graph branches): the
-// latency-bound weight GEMMs of one slice overlap the HBM-bound cross-attention of another.
-static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B, const wjb_decode_opts& o,
-                       const uint8_t* suppress_mask, int32_t* tokens, float* slp, float* nsp, int32_t* out_len, cudaStream_t s, int split) {
-    // experimental persistent step kernel: correct (parity-tested) but measured slower than the graph path on B200
-    // (11.1 vs 7.0 ms/step at B=64, large-v3), so it is opt-in
-    static const bool use_mega = getenv("WJB_DECODE_MEGA") != nullptr && atoi(getenv("WJB_DECODE_MEGA")) != 0;
-    const wjb_dims& dm = m->d;
-    if (use_mega && B <= 64 && dm.n_text_state <= 1280 && dm.n_text_state % 32 == 0) {
-        MegaLaunch ml;
-        ml.layers = w.mega_layers;
-        ml.n_layer = dm.n_text_layer;
-        ml.emb = m->h16("dec.emb");
-        ml.pos = m->h16("dec.pos");
-        ml.lnf_g = m->h16("dec.ln.g");
-        ml.lnf_b = m->h16("dec.ln.b");
-        ml.B = B;
-        ml.n = dm.n_text_state;
-        ml.H = dm.n_text_head;
-        ml.T = dm.n_audio_ctx;
-        ml.n_ctx = dm.n_text_ctx;
-        ml.n_vocab = dm.n_vocab;
-        ml.logits_stride = w.logits_stride;
-        ml.x = w.x;
-        ml.h = w.h;
-        ml.qkv = w.qkv;
-        ml.q = w.q;
-        ml.a = w.a;
-        ml.mlp = w.mlp;
-        ml.logits = w.logits;
-        ml.self_kv = w.self_kv;
-        ml.cross_kv = reinterpret_cast<const __half*>(cross_kv);
-        ml.tokens = tokens;
-        ml.tokens_stride = o.tokens_stride;
-        ml.ctl = w.ctl;
-        ml.done = w.done;
-        ml.bar = w.mega_bar;
-        ml.prof = getenv("WJB_MEGA_PROF") ? w.mega_prof : nullptr;
-        if (int e = launch_decode_mega(ml, s)) return e;
-        DecodeParams p;
-        p.B = B;
-        p.n_vocab = dm.n_vocab;
-        p.logits_stride = w.logits_stride;
-        p.eot = o.eot;
-        p.no_speech = o.no_speech;
-        p.no_timestamps = o.no_timestamps;
-        p.timestamp_begin = o.timestamp_begin;
-        p.suppress_blank = o.suppress_blank;
-        p.blank_token = o.blank_token;
-        p.apply_timestamp_rules = o.apply_timestamp_rules;
-        p.max_initial_timestamp_index = o.max_initial_timestamp_index;
-        p.n_ctx = dm.n_text_ctx;
-        p.tokens_stride = o.tokens_stride;
-        if (int e = launch_sample(w.logits, suppress_mask, tokens, nullptr, slp, nsp, out_len, w.done, w.ctl, p, s)) return e;
-        return launch_advance(w.ctl, s);
+    if (beam) {
+        if (int e = launch_beam_select(w.logits, suppress_mask, *beam, nsp, w.done, w.ctl, p, s)) return e;
+    } else {
+        p.trace_logits = m->trace_logits;
+        p.trace_sampled = m->trace_sampled;
+        p.trace_forced = m->trace_forced;
+        if (int e = launch_sample(w.logits, suppress_mask, tokens, slp, nsp, out_len, w.done, w.ctl, p, s)) return e;
     }
-    if (split > B) split = B;
-    if (split <= 1) {
-        if (int e = decode_branch(m, w, cross_kv, B, 0, B, 0, o, suppress_mask, tokens, slp, nsp, out_len, s)) return e;
-        return launch_advance(w.ctl, s);
-    }
-    cudaEventRecord(m->ev_fork, s);
-    int rc = 0;
-    for (int i = 0; i < split; ++i) {
-        const int b0 = (int)((long long)B * i / split), b1 = (int)((long long)B * (i + 1) / split);
-        cudaStream_t bs = (i == 0) ? s : m->br_stream[i];
-        if (i > 0) cudaStreamWaitEvent(bs, m->ev_fork, 0);
-        if (!rc) rc = decode_branch(m, w, cross_kv, B, b0, b1 - b0, i, o, suppress_mask, tokens, slp, nsp, out_len, bs);
-        if (i > 0) {
-            cudaEventRecord(m->ev_join[i], bs);
-            cudaStreamWaitEvent(s, m->ev_join[i], 0);
-        }
-    }
-    if (rc) return rc;
     return launch_advance(w.ctl, s);
 }
 
@@ -724,6 +614,7 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
                       size_t workspace_bytes, int* steps_run, void* stream) {
     if (!m || !cross_kv || !opts || !tokens || !sum_logprob || !no_speech_prob || !out_len || !workspace)
         return set_error("decode: null argument");
+    if (int e = ensure_init()) return e;
     const wjb_dims& d = m->d;
     // order after the caller's stream, then run on our own capturable stream; synchronous on return
     cudaStream_t s = m->own_stream;
@@ -739,104 +630,67 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
     if (o.tokens_stride < o.n_initial + o.sample_len) return set_error("decode: tokens_stride too small");
     DecWs w = dec_ws(d, batch, reinterpret_cast<uint8_t*>(workspace));
     if (w.total > workspace_bytes) return set_error("decode: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    if (m->trace_logits && m->trace_logits_bytes < (size_t)total_steps * batch * w.logits_stride * 2)
+        return set_error("decode: logits trace buffer too small (%zu < %zu)", m->trace_logits_bytes, (size_t)total_steps * batch * w.logits_stride * 2);
 
     // reset per-run state
-    DecodeCtl h_ctl;
-    h_ctl.step = 0;
-    h_ctl.n_initial = o.n_initial;
-    h_ctl.sot_index = o.sot_index;
-    h_ctl.max_steps = o.sample_len;
-    h_ctl.n_done = 0;
-    h_ctl.temperature = o.temperature;
-    h_ctl.seed = o.seed;
+    DecodeCtl* h_ctl = m->h_ctl;  // pinned: the async copy below may outlive this frame's locals
+    h_ctl->step = 0;
+    h_ctl->n_initial = o.n_initial;
+    h_ctl->sot_index = o.sot_index;
+    h_ctl->max_steps = o.sample_len;
+    h_ctl->n_done = 0;
+    h_ctl->temperature = o.temperature;
+    h_ctl->seed = o.seed;
     cudaError_t ce;
-    if ((ce = cudaMemcpyAsync(w.ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+    if ((ce = cudaMemcpyAsync(w.ctl, h_ctl, sizeof(*h_ctl), cudaMemcpyHostToDevice, s)) != cudaSuccess)
         return set_error("decode ctl copy: %s", cudaGetErrorString(ce));
-    {
-        std::vector<MegaLayer> tab(d.n_text_layer);
-        for (int i = 0; i < d.n_text_layer; ++i) {
-            const std::string p = "dec." + std::to_string(i) + ".";
-            MegaLayer& L = tab[i];
-            L.ln1_g = m->h16(p + "ln1.g");
-            L.ln1_b = m->h16(p + "ln1.b");
-            L.qkv_w = m->h16(p + "qkv.w");
-            L.qkv_b = m->h16(p + "qkv.b");
-            L.out_w = m->h16(p + "out.w");
-            L.out_b = m->h16(p + "out.b");
-            L.ln2_g = m->h16(p + "ln2.g");
-            L.ln2_b = m->h16(p + "ln2.b");
-            L.cq_w = m->h16(p + "cq.w");
-            L.cq_b = m->h16(p + "cq.b");
-            L.cout_w = m->h16(p + "cout.w");
-            L.cout_b = m->h16(p + "cout.b");
-            L.ln3_g = m->h16(p + "ln3.g");
-            L.ln3_b = m->h16(p + "ln3.b");
-            L.fc1_w = m->h16(p + "fc1.w");
-            L.fc1_b = m->h16(p + "fc1.b");
-            L.fc2_w = m->h16(p + "fc2.w");
-            L.fc2_b = m->h16(p + "fc2.b");
-        }
-        if ((ce = cudaMemcpyAsync(w.mega_layers, tab.data(), sizeof(MegaLayer) * tab.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess)
-            return set_error("decode table copy: %s", cudaGetErrorString(ce));
-        cudaStreamSynchronize(s);  // tab is a stack-lifetime host buffer
-    }
     cudaMemsetAsync(w.done, 0, batch, s);
-    for (int i = 0; i < wjb_model::kMaxSplit; ++i) cudaMemsetAsync(w.splitk + kSplitKSlot * i, 0, kSplitKCounters * sizeof(unsigned), s);
     cudaMemsetAsync(sum_logprob, 0, sizeof(float) * batch, s);
     cudaMemsetAsync(no_speech_prob, 0, sizeof(float) * batch, s);
     cudaMemsetAsync(out_len, 0, sizeof(int32_t) * batch, s);
-    // h_ctl lives on this stack frame: make sure the copy has been consumed before we return
-    const bool use_graph = getenv("WJB_NO_GRAPH") == nullptr;
-    int split = 1;  // measured on B200: batch-slice branches only pay off with the mma.sync GEMM (WJB_DECODE_SKINNY)
-    if (const char* e = getenv("WJB_DECODE_SPLIT")) split = atoi(e);
-    if (split < 1) split = 1;
-    if (split > wjb_model::kMaxSplit) split = wjb_model::kMaxSplit;
-    if (use_graph) {
-        const bool hit = m->graph && m->g_kv == cross_kv && m->g_ws == workspace && m->g_B == batch && m->g_mask == suppress_mask &&
-                         m->g_tokens == tokens && m->g_slp == sum_logprob && m->g_nsp == no_speech_prob && m->g_len == out_len &&
-                         m->g_split == split && memcmp(&m->g_opts, &okey, sizeof(okey)) == 0;
-        if (!hit) {
-            if (m->graph) {
-                cudaGraphExecDestroy(m->graph);
-                m->graph = nullptr;
-            }
-            cudaStreamSynchronize(s);
-            cudaGraph_t graph = nullptr;
-            if ((ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
-                return set_error("decode: begin capture: %s", cudaGetErrorString(ce));
-            static const bool want_pdl = getenv("WJB_NO_PDL") == nullptr;
-            set_pdl(want_pdl);
-            int e = decode_step(m, w, cross_kv, batch, o, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, s, split);
-            set_pdl(false);
-            ce = cudaStreamEndCapture(s, &graph);
-            if (e) {
-                if (graph) cudaGraphDestroy(graph);
-                return e;
-            }
-            if (ce != cudaSuccess) return set_error("decode: end capture: %s", cudaGetErrorString(ce));
-            ce = cudaGraphInstantiate(&m->graph, graph, 0);
-            cudaGraphDestroy(graph);
-            if (ce != cudaSuccess) return set_error("decode: graph instantiate: %s", cudaGetErrorString(ce));
-            m->g_kv = cross_kv;
-            m->g_ws = workspace;
-            m->g_B = batch;
-            m->g_mask = suppress_mask;
-            m->g_tokens = tokens;
-            m->g_slp = sum_logprob;
-            m->g_nsp = no_speech_prob;
-            m->g_len = out_len;
-            m->g_opts = okey;
-            m->g_split = split;
+    const bool hit = m->graph && m->g_kv == cross_kv && m->g_ws == workspace && m->g_B == batch && m->g_mask == suppress_mask &&
+                     m->g_tokens == tokens && m->g_slp == sum_logprob && m->g_nsp == no_speech_prob && m->g_len == out_len &&
+                     m->g_trace_logits == m->trace_logits && m->g_trace_sampled == m->trace_sampled && m->g_trace_forced == m->trace_forced &&
+                     memcmp(&m->g_opts, &okey, sizeof(okey)) == 0;
+    if (!hit) {
+        if (m->graph) {
+            cudaGraphExecDestroy(m->graph);
+            m->graph = nullptr;
         }
+        cudaStreamSynchronize(s);
+        cudaGraph_t graph = nullptr;
+        if ((ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
+            return set_error("decode: begin capture: %s", cudaGetErrorString(ce));
+        set_pdl(true);
+        int e = decode_step(m, w, cross_kv, batch, o, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, s);
+        set_pdl(false);
+        ce = cudaStreamEndCapture(s, &graph);
+        if (e) {
+            if (graph) cudaGraphDestroy(graph);
+            return e;
+        }
+        if (ce != cudaSuccess) return set_error("decode: end capture: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&m->graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return set_error("decode: graph instantiate: %s", cudaGetErrorString(ce));
+        m->g_kv = cross_kv;
+        m->g_ws = workspace;
+        m->g_B = batch;
+        m->g_mask = suppress_mask;
+        m->g_tokens = tokens;
+        m->g_slp = sum_logprob;
+        m->g_nsp = no_speech_prob;
+        m->g_len = out_len;
+        m->g_opts = okey;
+        m->g_trace_logits = m->trace_logits;
+        m->g_trace_sampled = m->trace_sampled;
+        m->g_trace_forced = m->trace_forced;
     }
     const int check_every = o.check_every > 0 ? o.check_every : 8;
     int step = 0;
     for (; step < total_steps; ++step) {
-        if (use_graph) {
-            if ((ce = cudaGraphLaunch(m->graph, s)) != cudaSuccess) return set_error("decode: graph launch: %s", cudaGetErrorString(ce));
-        } else {
-            if (int e = decode_step(m, w, cross_kv, batch, o, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, s, split)) return e;
-        }
+        if ((ce = cudaGraphLaunch(m->graph, s)) != cudaSuccess) return set_error("decode: graph launch: %s", cudaGetErrorString(ce));
         if ((step + 1) % check_every == 0 && step + 1 >= o.n_initial) {
             cudaMemcpyAsync(m->h_done, &w.ctl->n_done, sizeof(int), cudaMemcpyDeviceToHost, s);
             if ((ce = cudaStreamSynchronize(s)) != cudaSuccess) return set_error("decode: sync: %s", cudaGetErrorString(ce));
@@ -847,20 +701,6 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
         }
     }
     if ((ce = cudaStreamSynchronize(s)) != cudaSuccess) return set_error("decode: final sync: %s", cudaGetErrorString(ce));
-    if (getenv("WJB_MEGA_PROF")) {
-        const int per_layer = 11, n_stamp = 2 + per_layer * d.n_text_layer + 2;
-        std::vector<unsigned long long> t(n_stamp);
-        cudaMemcpy(t.data(), w.mega_prof, sizeof(unsigned long long) * n_stamp, cudaMemcpyDeviceToHost);
-        const char* names[per_layer] = {"ln1", "qkv", "self", "out", "ln2", "cq", "cross", "cout", "ln3", "fc1", "fc2"};
-        double acc[per_layer] = {0};
-        for (int l = 0; l < d.n_text_layer; ++l)
-            for (int k = 0; k < per_layer; ++k) acc[k] += double(t[2 + l * per_layer + k] - t[1 + l * per_layer + k]) * 1e-3;
-        fprintf(stderr, "wjb mega profile (last step, us summed over layers): embed %.1f", double(t[1] - t[0]) * 1e-3);
-        for (int k = 0; k < per_layer; ++k) fprintf(stderr, " %s %.1f", names[k], acc[k]);
-        const int base = 1 + per_layer * d.n_text_layer;
-        fprintf(stderr, " lnf %.1f logits %.1f total %.1f\n", double(t[base + 1] - t[base]) * 1e-3, double(t[base + 2] - t[base + 1]) * 1e-3,
-                double(t[base + 2] - t[0]) * 1e-3);
-    }
     if (steps_run) *steps_run = step;
     return 0;
 }
@@ -894,6 +734,7 @@ int wjb_decode_beam(wjb_model* m, const void* cross_kv, const wjb_beam_bufs* buf
     if (!bufs->tokens || !bufs->anc || !bufs->sum_logprob || !bufs->fin_tokens || !bufs->fin_score || !bufs->fin_len || !bufs->fin_count ||
         !bufs->audio_done)
         return set_error("decode_beam: null buffer");
+    if (int e = ensure_init()) return e;
     const wjb_dims& d = m->d;
     const wjb_decode_opts& o = *opts;
     const int n_audio = bufs->n_audio, beam = bufs->beam_size, rows = n_audio * beam;
@@ -925,36 +766,29 @@ int wjb_decode_beam(wjb_model* m, const void* cross_kv, const wjb_beam_bufs* buf
     bb.fin_count = bufs->fin_count;
     bb.audio_done = bufs->audio_done;
 
-    DecodeCtl h_ctl;
-    h_ctl.step = 0;
-    h_ctl.n_initial = o.n_initial;
-    h_ctl.sot_index = o.sot_index;
-    h_ctl.max_steps = o.sample_len;
-    h_ctl.n_done = 0;
-    h_ctl.temperature = 0.f;
-    h_ctl.seed = 0;
+    DecodeCtl* h_ctl = m->h_ctl;
+    h_ctl->step = 0;
+    h_ctl->n_initial = o.n_initial;
+    h_ctl->sot_index = o.sot_index;
+    h_ctl->max_steps = o.sample_len;
+    h_ctl->n_done = 0;
+    h_ctl->temperature = 0.f;
+    h_ctl->seed = 0;
     cudaError_t ce;
-    if ((ce = cudaMemcpyAsync(w.ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+    if ((ce = cudaMemcpyAsync(w.ctl, h_ctl, sizeof(*h_ctl), cudaMemcpyHostToDevice, s)) != cudaSuccess)
         return set_error("decode_beam ctl copy: %s", cudaGetErrorString(ce));
     cudaMemsetAsync(w.done, 0, rows, s);
-    for (int i = 0; i < wjb_model::kMaxSplit; ++i) cudaMemsetAsync(w.splitk + kSplitKSlot * i, 0, kSplitKCounters * sizeof(unsigned), s);
     cudaMemsetAsync(no_speech_prob, 0, sizeof(float) * n_audio, s);
     if ((ce = cudaStreamSynchronize(s)) != cudaSuccess) return set_error("decode_beam: setup sync: %s", cudaGetErrorString(ce));
 
     // one step as a CUDA graph (re-captured per call: its identity would be a dozen pointers and a run is hundreds of replays)
-    const bool use_graph = getenv("WJB_NO_GRAPH") == nullptr;
     cudaGraphExec_t exec = nullptr;
-    auto one_step = [&]() -> int {
-        if (int e = decode_branch(m, w, cross_kv, rows, 0, rows, 0, o, suppress_mask, nullptr, nullptr, no_speech_prob, nullptr, s, &bb)) return e;
-        return launch_advance(w.ctl, s);
-    };
-    if (use_graph) {
+    {
         cudaGraph_t graph = nullptr;
         if ((ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
             return set_error("decode_beam: begin capture: %s", cudaGetErrorString(ce));
-        static const bool want_pdl = getenv("WJB_NO_PDL") == nullptr;
-        set_pdl(want_pdl);
-        int e = one_step();
+        set_pdl(true);
+        int e = decode_step(m, w, cross_kv, rows, o, suppress_mask, nullptr, nullptr, no_speech_prob, nullptr, s, &bb);
         set_pdl(false);
         ce = cudaStreamEndCapture(s, &graph);
         if (e) {
@@ -969,12 +803,8 @@ int wjb_decode_beam(wjb_model* m, const void* cross_kv, const wjb_beam_bufs* buf
     const int check_every = o.check_every > 0 ? o.check_every : 8;
     int step = 0, rc = 0;
     for (; step < total_steps; ++step) {
-        if (use_graph) {
-            if ((ce = cudaGraphLaunch(exec, s)) != cudaSuccess) {
-                rc = set_error("decode_beam: graph launch: %s", cudaGetErrorString(ce));
-                break;
-            }
-        } else if ((rc = one_step()) != 0) {
+        if ((ce = cudaGraphLaunch(exec, s)) != cudaSuccess) {
+            rc = set_error("decode_beam: graph launch: %s", cudaGetErrorString(ce));
             break;
         }
         if ((step + 1) % check_every == 0 && step + 1 >= o.n_initial) {
@@ -999,11 +829,7 @@ int wjb_decode_beam(wjb_model* m, const void* cross_kv, const wjb_beam_bufs* buf
 int wjb_gemm_f16(const void* A, int64_t a_row_stride, int64_t a_batch_stride, int rows_per_batch, int n_batch, int K, const void* W,
                  int N, int ldw, const void* bias, const void* residual, void* out, int64_t out_row_stride, int64_t out_batch_stride,
                  int flags, int block_n, void* stream) {
-    if (block_n == -1) {  // weight-streaming variant (decoder steps)
-        if (n_batch != 1) return set_error("gemm: skinny variant needs n_batch == 1");
-        return launch_gemm_skinny((const __half*)A, (int)a_row_stride, (const __half*)W, ldw, (const __half*)bias, (const __half*)residual,
-                                  (__half*)out, (int)out_row_stride, rows_per_batch, N, K, flags & GEMM_GELU, (cudaStream_t)stream);
-    }
+    if (int e = ensure_init()) return e;
     GemmArgs g;
     g.A = (const __half*)A;
     g.a_row_stride = a_row_stride;
@@ -1024,7 +850,8 @@ int wjb_gemm_f16(const void* A, int64_t a_row_stride, int64_t a_batch_stride, in
     return launch_gemm(g, (cudaStream_t)stream);
 }
 
-size_t wjb_gemm_splitk_workspace_bytes(void) { return kSplitKSlot; }
+constexpr size_t kSplitKBytes = 8u << 20;
+size_t wjb_gemm_splitk_workspace_bytes(void) { return kSplitKCounters * sizeof(unsigned) + kSplitKBytes; }
 
 void wjb_debug_gemm_trace(void* buf) {
     gemm_set_trace(buf);
@@ -1034,7 +861,7 @@ void wjb_debug_gemm_trace(void* buf) {
 int wjb_gemm_step_ln_f16(const void* A, int64_t a_row_stride, int rows, int K, const void* ln_gamma, const void* ln_beta, const void* W, int N,
                          int ldw, const void* bias, const void* residual, void* out, int64_t out_row_stride, int flags, int block_n,
                          int cluster, int w_constant, void* stream) {
-    if (int e = init_kernels()) return e;
+    if (int e = ensure_init()) return e;
     StepGemmArgs g;
     g.A = (const __half*)A;
     g.a_row_stride = a_row_stride;
@@ -1067,6 +894,7 @@ void wjb_debug_set_pdl(int on) { set_pdl(on != 0); }
 int wjb_gemm_f16_splitk(const void* A, int64_t a_row_stride, int rows, int K, const void* W, int N, int ldw, const void* bias,
                         const void* residual, void* out, int64_t out_row_stride, int flags, int block_n, int splits, void* workspace,
                         size_t workspace_bytes, void* stream) {
+    if (int e = ensure_init()) return e;
     if (!workspace || workspace_bytes < kSplitKCounters * sizeof(unsigned) + (1u << 20)) return set_error("gemm split-K: workspace too small");
     GemmArgs g;
     g.A = (const __half*)A;
@@ -1090,22 +918,23 @@ int wjb_gemm_f16_splitk(const void* A, int64_t a_row_stride, int rows, int K, co
     return launch_gemm(g, (cudaStream_t)stream);
 }
 
-void wjb_gemm_skinny_config(int nt, int ks) { skinny_config(nt, ks); }
-
 int wjb_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int n, void* stream) {
+    if (int e = ensure_init()) return e;
     return launch_layernorm((const __half*)x, (const __half*)gamma, (const __half*)beta, (__half*)out, rows, n, (cudaStream_t)stream);
 }
 
 int wjb_attention_encoder_f16(const void* qkv, void* out, int batch, int T, int n_head, void* stream) {
-    if (int e = init_kernels()) return e;
+    if (int e = ensure_init()) return e;
     return launch_attn_encoder((const __half*)qkv, (__half*)out, batch, T, n_head, (cudaStream_t)stream);
 }
 
 int wjb_attention_self_f16(const void* qkv, void* kv_cache, void* out, const int32_t* position, int batch, int n_head, int n_ctx, void* stream) {
+    if (int e = ensure_init()) return e;
     return launch_attn_dec_self((const __half*)qkv, (__half*)kv_cache, (__half*)out, position, nullptr, batch, n_head, n_ctx, (cudaStream_t)stream);
 }
 
 int wjb_attention_cross_f16(const void* q, const void* kv, void* out, int batch, int n_head, int T, void* stream) {
+    if (int e = ensure_init()) return e;
     return launch_attn_dec_cross((const __half*)q, (const __half*)kv, (__half*)out, nullptr, batch, n_head, T, (cudaStream_t)stream);
 }
 

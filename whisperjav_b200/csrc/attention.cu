@@ -419,122 +419,11 @@ int launch_attn_dec_self(const __half* qkv, __half* kv_cache, __half* out, const
 }
 
 // ============================================================================ decoder cross-attention
-// One CTA (128 threads) per (b, head); K and V are [T][64] fp16, streamed once each.
+// One CTA (128 threads) per (b, head) (or per (window, head) with NQ beams); K and V are [T][64] fp16, streamed once each.
 constexpr int kCrossThreads = 128;
 constexpr int kCrossMaxT = 1536;
 
-__global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
-                                                                        __half* __restrict__ out,
-                                                                        const unsigned char* __restrict__ done, int H, int T, int kv_div) {
-    pdl_prologue();
-    const int h = blockIdx.x, b = blockIdx.y;
-    if (done && done[b]) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = H * 64;
-    __shared__ float sc[kCrossMaxT];
-    __shared__ float red[8];
-    __shared__ float osum[4][64];
-    const int bk = b / kv_div;  // beam search: the rows of one window share its K/V
-    const uint4* K = reinterpret_cast<const uint4*>(kv + ((long long)(bk * 2 * H + h) * T) * 64);
-    const uint4* V = reinterpret_cast<const uint4*>(kv + ((long long)(bk * 2 * H + H + h) * T) * 64);
-    const int chunk = tid & 7;   // which 16-byte (8 dims) slice of the 64-dim row
-    const int slot = tid >> 3;   // key slot 0..15 within an iteration
-    float qf[8];
-    {
-        uint4 u = reinterpret_cast<const uint4*>(q + (long long)b * n + h * 64)[chunk];
-        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float2 f = __half22float2(h2[j]);
-            qf[2 * j] = f.x;
-            qf[2 * j + 1] = f.y;
-        }
-    }
-    // ---- scores
-    for (int t0 = 0; t0 < T; t0 += 64) {
-        uint4 u[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int t = t0 + r * 16 + slot;
-            u[r] = (t < T) ? __ldg(K + (long long)t * 8 + chunk) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const __half2* h2 = reinterpret_cast<const __half2*>(&u[r]);
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float2 f = __half22float2(h2[j]);
-                s = fmaf(qf[2 * j], f.x, s);
-                s = fmaf(qf[2 * j + 1], f.y, s);
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            const int t = t0 + r * 16 + slot;
-            if (chunk == 0 && t < T) sc[t] = s * 0.125f;
-        }
-    }
-    __syncthreads();
-    // ---- softmax over T scores
-    float mx = -INFINITY;
-    for (int t = tid; t < T; t += kCrossThreads) mx = fmaxf(mx, sc[t]);
-    mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-    float sum = 0.f;
-    for (int t = tid; t < T; t += kCrossThreads) {
-        const float e = __expf(sc[t] - mx);
-        sc[t] = e;
-        sum += e;
-    }
-    sum = warp_sum(sum);
-    if (lane == 0) red[4 + warp] = sum;
-    __syncthreads();
-    const float inv = 1.0f / (red[4] + red[5] + red[6] + red[7]);
-    // ---- out = sum_t p[t] V[t]
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int t0 = 0; t0 < T; t0 += 64) {
-        uint4 u[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int t = t0 + r * 16 + slot;
-            u[r] = (t < T) ? __ldg(V + (long long)t * 8 + chunk) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int t = t0 + r * 16 + slot;
-            const float w = (t < T) ? round_f16(sc[t] * inv) : 0.f;
-            const __half2* h2 = reinterpret_cast<const __half2*>(&u[r]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float2 f = __half22float2(h2[j]);
-                acc[2 * j] = fmaf(w, f.x, acc[2 * j]);
-                acc[2 * j + 1] = fmaf(w, f.y, acc[2 * j + 1]);
-            }
-        }
-    }
-    // reduce over the 4 key slots inside a warp (lane bits 3,4), then over the 4 warps
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
-        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
-    }
-    if (lane < 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) osum[warp][lane * 8 + j] = acc[j];
-    }
-    __syncthreads();
-    if (tid < 64) {
-        const float v = osum[0][tid] + osum[1][tid] + osum[2][tid] + osum[3][tid];
-        out[(long long)b * n + h * 64 + tid] = __float2half_rn(v);
-    }
-}
-
-// ---- bulk-copy variant: K and V stream through a 4-stage smem ring filled by cp.async.bulk (one elected thread, mbarrier
+// K and V stream through a 4-stage smem ring filled by cp.async.bulk (one elected thread, mbarrier
 // completion), so the bytes in flight are not bounded by the LSU's outstanding-request capacity; V chunks are already in
 // flight while the softmax runs.
 constexpr int kCbStages = 4, kCbKeys = 128, kCbStageBytes = kCbKeys * 128;
@@ -704,12 +593,6 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
 template <int NQ>
 static int launch_cross_bulk(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T, int kv_div,
                              cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_dec_cross_bulk_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, cb_smem_bytes(NQ));
-        if (e != cudaSuccess) return set_error("cross attr: %s", cudaGetErrorString(e));
-        attr = true;
-    }
     dim3 grid(H, B / NQ);
     cudaError_t e = launch_k(attn_dec_cross_bulk_kernel<NQ>, grid, dim3(kCrossThreads), (size_t)cb_smem_bytes(NQ), s, q, kv, out, done, H, T, kv_div);
     if (e != cudaSuccess) return set_error("attn_dec_cross_bulk launch: %s", cudaGetErrorString(e));
@@ -731,23 +614,15 @@ int launch_attn_dec_cross(const __half* q, const __half* kv, __half* out, const 
                           cudaStream_t s, int kv_div) {
     if (kv_div < 1) kv_div = 1;
     if (T > kCrossMaxT) return set_error("attn_dec_cross: T %d > %d", T, kCrossMaxT);
-    static const bool use_bulk = getenv("WJB_CROSS_LSU") == nullptr;
-    if (use_bulk) {
-        // beam search: the beams of a window share one pass over its K/V when they fit one CTA
-        static const bool share = !(getenv("WJB_CROSS_SHARE") && atoi(getenv("WJB_CROSS_SHARE")) == 0);
-        if (share && kv_div > 1 && kv_div <= kCbMaxQ && B % kv_div == 0) {
-            switch (kv_div) {
-                case 2: return launch_cross_bulk<2>(q, kv, out, done, B, H, T, kv_div, s);
-                case 3: return launch_cross_bulk<3>(q, kv, out, done, B, H, T, kv_div, s);
-                case 4: return launch_cross_bulk<4>(q, kv, out, done, B, H, T, kv_div, s);
-            }
+    // beam search: the beams of a window share one pass over its K/V when they fit one CTA
+    if (kv_div > 1 && kv_div <= kCbMaxQ && B % kv_div == 0) {
+        switch (kv_div) {
+            case 2: return launch_cross_bulk<2>(q, kv, out, done, B, H, T, kv_div, s);
+            case 3: return launch_cross_bulk<3>(q, kv, out, done, B, H, T, kv_div, s);
+            case 4: return launch_cross_bulk<4>(q, kv, out, done, B, H, T, kv_div, s);
         }
-        return launch_cross_bulk<1>(q, kv, out, done, B, H, T, kv_div, s);
     }
-    dim3 grid(H, B);
-    launch_k(attn_dec_cross_kernel, grid, dim3(kCrossThreads), 0, s, q, kv, out, done, H, T, kv_div);
-    WJB_CHECK_LAUNCH("attn_dec_cross");
-    return 0;
+    return launch_cross_bulk<1>(q, kv, out, done, B, H, T, kv_div, s);
 }
 
 }  // namespace wjb

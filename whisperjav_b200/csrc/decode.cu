@@ -332,6 +332,10 @@ sample_kernel(const __half* __restrict__ logits, const unsigned char* __restrict
     const int V = p.n_vocab;
     const __half* row = logits + (long long)b * p.logits_stride;
     for (int v = tid; v < V; v += kSampleThreads) srow[v] = row[v];
+    if (p.trace_logits) {
+        __half* dst = p.trace_logits + ((long long)step * p.B + b) * p.logits_stride;
+        for (int v = tid; v < V; v += kSampleThreads) dst[v] = row[v];
+    }
     int* trow = tokens + (long long)b * p.tokens_stride;
     if (tid == 0) {
         int last_ts = 0, pen_ts = 0, have = 0, tl = 0;
@@ -446,7 +450,9 @@ sample_kernel(const __half* __restrict__ logits, const unsigned char* __restrict
         pick = block_argmax(g, sh_am);
     }
     if (tid == 0) {
-        const int tok = pick.i;
+        int tok = pick.i;
+        if (p.trace_sampled && cur_len < p.tokens_stride) p.trace_sampled[(long long)b * p.tokens_stride + cur_len] = tok;
+        if (p.trace_forced && cur_len < p.tokens_stride) tok = p.trace_forced[(long long)b * p.tokens_stride + cur_len];
         const float lse = ts_wins ? mx + logf(s_ts) : mx + logf(s_text + s_ts);
         const float lp = __half2float(srow[tok]) - lse;
         sum_logprob[b] += lp;
@@ -466,16 +472,9 @@ __global__ void advance_kernel(DecodeCtl* ctl) {
     ctl->step += 1;
 }
 
-int launch_sample(const __half* logits, const unsigned char* suppress_mask, int* tokens, const int* /*initial_tokens*/,
-                  float* sum_logprob, float* no_speech_prob, int* out_len, unsigned char* done, DecodeCtl* ctl, const DecodeParams& p,
+int launch_sample(const __half* logits, const unsigned char* suppress_mask, int* tokens, float* sum_logprob, float* no_speech_prob, int* out_len, unsigned char* done, DecodeCtl* ctl, const DecodeParams& p,
                   cudaStream_t s) {
     const size_t smem = ((size_t)p.n_vocab * 2 + 15) & ~size_t(15);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-        if (e != cudaSuccess) return set_error("sample attr: %s", cudaGetErrorString(e));
-        attr = true;
-    }
     if (smem > 110 * 1024) return set_error("sample: vocab %d too large", p.n_vocab);
     launch_k(sample_kernel, dim3(p.B), dim3(kSampleThreads), smem, s, logits, suppress_mask, tokens, sum_logprob, no_speech_prob, out_len, done, ctl, p);
     WJB_CHECK_LAUNCH("sample");

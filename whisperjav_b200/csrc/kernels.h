@@ -7,6 +7,7 @@ namespace wjb {
 // ---- error plumbing (api.cu) -------------------------------------------------------------
 int set_error(const char* fmt, ...);  // records the message, returns a non-zero status
 int sm_count();
+int ensure_init();  // per-device kernel attribute set-up (api.cu)
 typedef CUresult (*tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                          CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -91,12 +92,6 @@ bool gemm_step_supported(int rows, int N, int K);
 int launch_gemm_step(const StepGemmArgs& a, cudaStream_t stream);
 int gemm_step_init();
 void gemm_step_set_trace(void* buf);
-// weight-streaming variant for <= 64 activation rows (decoder steps), gemm_skinny.cu
-int launch_gemm_skinny(const __half* x, int ldx, const __half* W, int ldw, const __half* bias, const __half* residual, __half* out,
-                       int ld_out, int M, int N, int K, int flags, cudaStream_t s);
-
-void skinny_config(int nt, int ks);
-
 // ---- elementwise / normalisation (elementwise.cu) ------------------------------------------
 int launch_layernorm(const __half* x, const __half* gamma, const __half* beta, __half* out, int rows, int n, cudaStream_t s);
 int launch_im2col_k3(const __half* xpad, __half* out, int B, int T_out, int C, int stride, int T_in_padded, cudaStream_t s);
@@ -150,6 +145,11 @@ struct DecodeParams {
     int suppress_blank, blank_token, apply_timestamp_rules, max_initial_timestamp_index;  // -1 = none
     int n_ctx;
     int tokens_stride;        // ints per row in tokens[]
+    // test / diagnostic hook (all null in production): raw logits [step][B][logits_stride], the ids the kernel picked
+    // [B][tokens_stride], ids to feed instead (teacher forcing) [B][tokens_stride]
+    __half* trace_logits = nullptr;
+    int* trace_sampled = nullptr;
+    const int* trace_forced = nullptr;
 };
 int launch_embed(const int* tokens, int tokens_stride, const __half* emb, const __half* pos, __half* x, const DecodeCtl* ctl, int B,
                  int n, cudaStream_t s, long long parity_stride = 0);
@@ -170,33 +170,10 @@ struct BeamBufs {
 };
 int launch_beam_select(const __half* logits, const unsigned char* suppress_mask, const BeamBufs& bb, float* no_speech_prob,
                        unsigned char* done, DecodeCtl* ctl, const DecodeParams& p, cudaStream_t s);
-int launch_sample(const __half* logits, const unsigned char* suppress_mask, int* tokens, const int* initial_tokens, float* sum_logprob,
+int launch_sample(const __half* logits, const unsigned char* suppress_mask, int* tokens, float* sum_logprob,
                   float* no_speech_prob, int* out_len, unsigned char* done, DecodeCtl* ctl, const DecodeParams& p, cudaStream_t s);
 
 int launch_advance(DecodeCtl* ctl, cudaStream_t s);
-
-// ---- persistent decoder-step kernel (decode_mega.cu) -----------------------------------------
-struct MegaLayer {  // device-resident table, one entry per decoder layer
-    const __half *ln1_g, *ln1_b, *qkv_w, *qkv_b, *out_w, *out_b;
-    const __half *ln2_g, *ln2_b, *cq_w, *cq_b, *cout_w, *cout_b;
-    const __half *ln3_g, *ln3_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
-};
-struct MegaLaunch {
-    const MegaLayer* layers;  // device pointer
-    int n_layer;
-    const __half *emb, *pos, *lnf_g, *lnf_b;
-    int B, n, H, T, n_ctx, n_vocab, logits_stride;
-    __half *x, *h, *qkv, *q, *a, *mlp, *logits;
-    __half* self_kv;
-    const __half* cross_kv;
-    const int* tokens;
-    int tokens_stride;
-    const DecodeCtl* ctl;
-    const unsigned char* done;
-    unsigned* bar;  // device counter for the grid barrier
-    unsigned long long* prof;  // optional per-phase timestamps (debug), >= 512 entries
-};
-int launch_decode_mega(const MegaLaunch& m, cudaStream_t s);
 
 // ---- VAD (vad.cu) --------------------------------------------------------------------------
 struct VadArgs;

@@ -234,12 +234,6 @@ __global__ void logmel_floor_kernel(const LogmelArgs a) {
 int launch_logmel(const LogmelArgs& a, cudaStream_t s) {
     if (a.n_mels > 128 || a.n_mels % 8) return set_error("logmel: n_mels=%d unsupported (<=128, multiple of 8)", a.n_mels);
     if (a.n_clips <= 0 || a.n_frames <= 0) return 0;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem));
-        if (e != cudaSuccess) return set_error("logmel attr: %s", cudaGetErrorString(e));
-        attr = true;
-    }
     cudaError_t e = cudaMemsetAsync(a.clip_max, 0, sizeof(float) * a.n_clips, s);
     if (e != cudaSuccess) return set_error("logmel memset: %s", cudaGetErrorString(e));
     mel_range_kernel<<<1, 128, 0, s>>>(a.filters, a.n_mels, a.mel_range);
@@ -250,6 +244,12 @@ int launch_logmel(const LogmelArgs& a, cudaStream_t s) {
     dim3 grid2(64, a.n_clips);
     logmel_floor_kernel<<<grid2, 256, 0, s>>>(a);
     WJB_CHECK_LAUNCH("logmel_floor");
+    return 0;
+}
+
+int logmel_init() {
+    cudaError_t e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem));
+    if (e != cudaSuccess) return set_error("logmel attr: %s", cudaGetErrorString(e));
     return 0;
 }
 

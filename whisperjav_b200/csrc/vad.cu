@@ -195,6 +195,12 @@ __global__ void __launch_bounds__(512) vad_lstm_kernel(const float* __restrict__
     }
 }
 
+int vad_init() {
+    cudaError_t e = cudaFuncSetAttribute(vad_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VadSmem));
+    if (e != cudaSuccess) return set_error("vad attr: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 }  // namespace wjb
 
 using namespace wjb;
@@ -209,12 +215,7 @@ int wjb_vad_forward(const float* audio, int64_t audio_stride, const int32_t* n_s
     if (!audio || !n_samples || !weights || !probs || !workspace) return set_error("vad: null argument");
     if (n_clips <= 0 || n_windows <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(vad_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VadSmem));
-        if (e != cudaSuccess) return set_error("vad attr: %s", cudaGetErrorString(e));
-        attr = true;
-    }
+    if (int e = ensure_init()) return e;
     float* gx = reinterpret_cast<float*>(workspace);
     dim3 grid((n_windows + kTile - 1) / kTile, n_clips);
     vad_features_kernel<<<grid, kFeatThreads, sizeof(VadSmem), s>>>(audio, audio_stride, n_samples, reinterpret_cast<const float*>(weights), gx,
