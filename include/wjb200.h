@@ -73,6 +73,10 @@ size_t wjb_encoder_workspace_bytes(const wjb_model* m, int batch);
 int wjb_encoder_forward(wjb_model* m, const void* mel_tm, int batch, void* out, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* Parity-test hook: while `out` is non-NULL every following wjb_encoder_forward also copies the residual stream after blocks
+ * every, 2*every, ... (1-based) to out[k][B][n_audio_ctx][n_audio_state] fp16 (k = block / every - 1); NULL = off. */
+int wjb_encoder_set_tap(wjb_model* m, void* out, int every);
+
 /* ---- cross-attention K/V projection (once per window) ---------------------------------------
  * Replaces the first-step `cross_attn.key/value(xa)` Linear calls cached by the KV hooks
  * [whisper/model.py::MultiHeadAttention.forward, whisper/decoding.py::PyTorchInference].

@@ -41,7 +41,8 @@ def test_segmenter_surface_and_postprocess():
     assert r.method == "b200-vad" and r.num_segments == 2 and r.num_groups == 2
     seg = r.segments[0]
     # padding: start - 11200 samples, end + 20800 samples (silero.py:286-297) on top of the hysteresis regions
-    assert seg.start_sample == max(0, int((100 * 512 - 480) ) - 11200 + 0) or seg.start_sample >= 0
+    assert (seg.start_sample, seg.end_sample) == (100 * 512 - 11200, 200 * 512 + 20800)
+    assert (r.segments[1].start_sample, r.segments[1].end_sample) == (400 * 512 - 11200, 500 * 512 + 20800)
     assert r.segments[1].start_sample >= r.segments[0].end_sample
     assert r.to_legacy_format()[0][0]["start"] == seg.start_sample
     t = B200SpeechSegmenter(threshold=0.5, style="ten", min_silence_duration_ms=100, chunk_threshold_s=1.0)

@@ -1,26 +1,31 @@
-"""Model-level parity on the GPU: CUDA path (through the C-ABI) vs the CPU oracle on the same seeded
-synthetic weights and audio.  Tolerances are north_star's: mel <= 1e-3 abs, encoder hidden states
-<= 1e-2 relative (fp16), greedy token ids identical (up to the first oracle near-tie, reported)."""
+"""Model-level parity on the GPU (tiny architecture, every decode mode): CUDA path through the C-ABI vs the CPU oracle on the
+same seeded synthetic weights and audio.  north_star tolerances: mel <= 1e-3 abs, encoder hidden states <= 1e-2 relative (fp16),
+greedy token ids identical.  Token identity is judged by oracle/parity.py: the oracle is teacher-forced along the device's own
+sequence, every step's raw logits are compared (<= LOGIT_QUANTA fp16 quanta), and every device token must be the oracle's
+arg-max on that prefix -- or, counted and bounded, a tie within TIE_QUANTA quanta of it.  The same checks at whisper-large-v3
+size are in tests/test_gpu_large_v3.py."""
 import json
+from pathlib import Path
 
 import numpy as np
 import pytest
 import torch
 
+from oracle import parity as P
 from oracle import whisper_oracle as wo
 from whisperjav_b200 import model as M
-from whisperjav_b200.synth import DIMS, speech_shaped_audio, synth_weights
+from whisperjav_b200.synth import DIMS, speech_shaped_audio, synth_preset, synth_weights
 
 pytestmark = pytest.mark.gpu
-NEAR_TIE = 0.08  # oracle top-2 logit margin (5 fp16 quanta at |logit| ~ 16) below which a divergence is not counted as a failure
+G = Path(__file__).parent / "golden"
 
 
 @pytest.fixture(scope="module")
 def tiny():
     dims = DIMS["tiny"]
-    w = synth_weights(dims, seed=7)
+    w = synth_weights(dims, **synth_preset("tiny"))
     m = M.WhisperB200(dims, w, max_batch=8)
-    return dims, w, m
+    return dims, w, m, wo.prepare_weights(w, True)
 
 
 @pytest.fixture(scope="module")
@@ -28,114 +33,153 @@ def clips():
     return [speech_shaped_audio(s, 1000 + i) for i, s in enumerate([30.0, 12.0, 5.0, 21.7])]
 
 
-def _oracle_mel_windows(clips, dims):
-    return torch.stack([wo.pad_or_trim(wo.log_mel_spectrogram(a, dims.n_mels, padding=wo.N_SAMPLES)[:, : len(a) // 160], wo.N_FRAMES)
-                        for a in clips])
-
-
-def _gpu_mel(m, clips):
-    S = max(len(c) for c in clips)
-    audio = torch.zeros(len(clips), S)
-    for i, c in enumerate(clips):
-        audio[i, : len(c)] = torch.from_numpy(c)
-    ns = torch.tensor([len(c) for c in clips], dtype=torch.int32)
-    return m.log_mel(audio.cuda(), ns.cuda(), n_frames=3000, layout="time")
-
-
 def test_mel_windows_match_oracle(tiny, clips):
-    dims, w, m = tiny
-    mel_tm = _gpu_mel(m, clips)
+    dims, w, m, pw = tiny
+    mel_tm = P.gpu_mel(m, clips)
     got = mel_tm[:, 1:-1].permute(0, 2, 1).float().cpu()
-    ref = _oracle_mel_windows(clips, dims)
-    assert (got - ref).abs().max().item() <= 1e-3
+    assert (got - P.oracle_mel_windows(clips, dims)).abs().max().item() <= 1e-3
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_mel_hf_semantics_match_hf_fixture(n_mels):
+    """The HF / anime path (generators/anime_whisper.py:256: WhisperProcessor pads the raw audio to 30 s, then reflect-pads):
+    the CUDA kernel with reflect_total=480000 against WhisperFeatureExtractor's own output (tests/golden/hf_logmel_*.npz)."""
+    z = np.load(G / f"hf_logmel_{n_mels}.npz")
+    dims = DIMS["tiny"] if n_mels == 80 else DIMS["large-v3"]
+    lib_model = M.WhisperB200.__new__(M.WhisperB200)  # log_mel needs only the library, the filterbank and a device
+    from whisperjav_b200 import _lib
+    lib_model.lib, lib_model.dims, lib_model.device, lib_model._bufs = _lib.load(), dims, torch.device("cuda:0"), {}
+    lib_model._filters = torch.from_numpy(M.slaney_mel_filters(n_mels)).cuda()
+    a = speech_shaped_audio(12.0, 1001)
+    audio = torch.zeros(1, 480000)
+    audio[0, : len(a)] = torch.from_numpy(a)
+    ns = torch.tensor([480000], dtype=torch.int32)   # HF: the zero padding is part of the signal
+    mel = lib_model.log_mel(audio.cuda(), ns.cuda(), n_frames=3000, layout="mel", reflect_total=480000)
+    got = mel[0].float().cpu().numpy()
+    assert np.abs(got[:, z["frames"]] - z["mel"]).max() <= 1e-3
 
 
 def test_encoder_matches_oracle(tiny, clips, diag_dir):
-    dims, w, m = tiny
-    mel_tm = _gpu_mel(m, clips[:2])
-    xa = m.encode(mel_tm).float().cpu()
-    # feed the oracle the *same* fp16 mel the GPU consumed, so only the encoder is compared
-    mel_in = mel_tm[:, 1:-1].permute(0, 2, 1).float().cpu()
-    ref = wo.encoder_forward(w, dims, mel_in, sim_fp16=True)
-    rel = ((xa - ref).norm() / ref.norm()).item()
-    mx = (xa - ref).abs().max().item()
-    (diag_dir / "encoder_tiny.json").write_text(json.dumps({"rel_fro": rel, "max_abs": mx, "ref_absmax": ref.abs().max().item()}))
-    assert rel <= 1e-2, (rel, mx)
-    assert mx <= 1e-2 * ref.abs().max().item() + 3e-2, mx
-
-
-def _compare_tokens(res_gpu, res_ref):
-    report = []
-    for b, (g, r) in enumerate(zip(res_gpu, res_ref)):
-        n = min(len(g.tokens), len(r.tokens))
-        div = next((i for i in range(n) if g.tokens[i] != r.tokens[i]), None)
-        if div is None and len(g.tokens) != len(r.tokens):
-            div = n
-        margin = r.margins[div] if div is not None and div < len(r.margins) else None
-        report.append({"b": b, "len_gpu": len(g.tokens), "len_ref": len(r.tokens), "first_divergence": div,
-                       "oracle_margin_at_divergence": margin, "min_margin": min(r.margins) if r.margins else None,
-                       "avg_logprob_gpu": g.avg_logprob, "avg_logprob_ref": r.avg_logprob,
-                       "no_speech_gpu": g.no_speech_prob, "no_speech_ref": r.no_speech_prob})
-    return report
+    dims, w, m, pw = tiny
+    rep, _ = P.encoder_parity(m, w, dims, P.gpu_mel(m, clips[:2]), tap_every=2, prepared=pw)
+    (diag_dir / "encoder_tiny.json").write_text(json.dumps(rep))
+    assert rep["ok"], rep
+    assert rep["max_abs"] <= 1e-2 * rep["ref_absmax"] + 3e-2, rep
 
 
 @pytest.mark.parametrize("without_timestamps", [False, True])
 def test_greedy_tokens_match_oracle(tiny, clips, diag_dir, without_timestamps):
-    dims, w, m = tiny
-    mel_tm = _gpu_mel(m, clips)
-    xa = m.encode(mel_tm)
-    res = m.decode_features(xa, language="ja", without_timestamps=without_timestamps, max_initial_timestamp=0.0)
-    # the oracle decodes from the GPU's own encoder output so that only the decoder path is compared
-    opts = wo.DecodingOptions(language="ja", without_timestamps=without_timestamps, max_initial_timestamp=0.0)
-    ref = wo.decode(w, dims, None, opts, True, audio_features=xa.float().cpu())
-    report = _compare_tokens(res, ref)
-    (diag_dir / f"tokens_tiny_wt{int(without_timestamps)}.json").write_text(json.dumps(report, indent=1))
-    assert len({tuple(r.tokens) for r in ref}) > 1, "degenerate oracle trajectories"
-    identical = 0
-    for rep, g, r in zip(report, res, ref):
-        if rep["first_divergence"] is None:
-            identical += 1
-            # logits are fp16 (upstream: fp16 matmul output, then .float()): one quantum is 2^-6 at |logit| ~ 16
-            assert abs(g.avg_logprob - r.avg_logprob) <= 2e-2
-            assert abs(g.no_speech_prob - r.no_speech_prob) <= 1e-3 + 0.02 * r.no_speech_prob
-        else:
-            assert rep["oracle_margin_at_divergence"] is not None and rep["oracle_margin_at_divergence"] < NEAR_TIE, rep
-    assert identical >= len(ref) - 1, report
+    """Decoder-only: the oracle decodes from the GPU's own encoder output."""
+    dims, w, m, pw = tiny
+    xa = m.encode(P.gpu_mel(m, clips))
+    rep = P.decode_parity(m, w, dims, xa, prepared=pw, language="ja", without_timestamps=without_timestamps, max_initial_timestamp=0.0)
+    (diag_dir / f"tokens_tiny_wt{int(without_timestamps)}.json").write_text(json.dumps(rep, indent=1))
+    assert rep["ok"], rep["failures"]
+    assert len({tuple(t) for t in rep["tokens"]}) == len(clips), "degenerate trajectories"
+    assert rep["tie_breaks"] <= max(1, rep["steps_checked"] // 100), rep          # near-ties are rare ...
+    assert rep["identical_windows"] >= rep["windows"] - 1, rep                   # ... and at most one window has any
+
+
+def test_teacher_forced_logits_match_oracle(tiny, clips, diag_dir):
+    """The reverse direction: the oracle decodes freely, the device is teacher-forced along the oracle's tokens and its raw
+    logits at every step are compared; the ids the device *would* have picked must agree wherever the oracle's margin is clear."""
+    dims, w, m, pw = tiny
+    xa = m.encode(P.gpu_mel(m, clips))
+    kw = dict(language="ja", max_initial_timestamp=0.0)
+    ref, rl = wo.decode(pw, dims, None, wo.DecodingOptions(**kw), True, audio_features=xa.float().cpu(), return_logits=True)
+    res, tr = m.decode_trace(xa, forced_tokens=[r.tokens for r in ref], **kw)
+    n0 = tr["n_initial"]
+    worst = 0.0
+    for b, r in enumerate(ref):
+        assert res[b].tokens == r.tokens                                   # the device followed the forced sequence
+        for i in range(min(len(r.tokens) + 1, len(rl))):
+            q = P.fp16_quantum(float(rl[i][b].max()))
+            d = float((tr["logits"][n0 - 1 + i, b] - rl[i][b]).abs().max()) / q
+            worst = max(worst, d)
+            picked = int(tr["sampled"][b, n0 + i])
+            want = (r.tokens + [P.opts_eot(dims)])[i]
+            if r.margins[i] > 8 * q:
+                assert picked == want, (b, i, picked, want, r.margins[i])
+        assert abs(res[b].sum_logprob - r.sum_logprob) <= 0.02 * (len(r.tokens) + 1)
+    (diag_dir / "teacher_forced_tiny.json").write_text(json.dumps({"dlogit_quanta_max": worst}))
+    assert worst <= 6.0, worst
 
 
 def test_transcribe_matches_oracle(tiny, clips, diag_dir):
-    """End to end (mel + encoder + decoder + seek loop all on the GPU vs all on the CPU).  The two encoders
-    agree to ~4e-3 relative, which moves logits by a few fp16 quanta, so token identity is required up to
-    the first step whose oracle top-2 margin is below NEAR_TIE_E2E."""
-    NEAR_TIE_E2E = 0.15
-    dims, w, m = tiny
+    """End to end (mel + encoder + decoder + seek loop all on the GPU vs all on the CPU): segments, seeks and token ids of whole
+    clips.  The two encoders differ by ~1e-3 relative, so a step whose oracle margin is within a few quanta can legitimately
+    flip; a clip is therefore compared token by token up to its first divergence, the divergence must be such a near-tie
+    (checked on the oracle's own logits), and most clips must have none."""
+    dims, w, m, pw = tiny
     kw = dict(language="ja", task="transcribe", temperature=0.0, no_speech_threshold=0.6, logprob_threshold=-1.0,
               compression_ratio_threshold=2.4, condition_on_previous_text=False, max_initial_timestamp=0.0)
-    got = m.transcribe_batch(clips[:3], **kw)
-    report = []
-    for a, g in zip(clips[:3], got):
-        ref = wo.transcribe(w, dims, a, **kw)
-        mel = wo.pad_or_trim(wo.log_mel_spectrogram(a, dims.n_mels, padding=wo.N_SAMPLES)[:, : len(a) // 160], wo.N_FRAMES)
-        first = wo.decode(w, dims, mel[None], wo.DecodingOptions(language="ja", max_initial_timestamp=0.0), True)[0]
-        gt = [t for s_ in g["segments"] for t in s_["tokens"]]
-        rt = [t for s_ in ref["segments"] for t in s_["tokens"]]
-        n = min(len(gt), len(rt), len(first.tokens))
-        div = next((i for i in range(n) if gt[i] != rt[i]), None)
-        report.append({"gpu": gt[:40], "ref": rt[:40], "div": div, "margin": first.margins[div] if div is not None else None})
-        assert g["language"] == "ja" and all(s_["end"] >= s_["start"] for s_ in g["segments"])
-        if div is not None:
-            assert first.margins[div] < NEAR_TIE_E2E, report[-1]
-        else:
-            assert [round(s_["start"], 2) for s_ in g["segments"]][:2] == [round(s_["start"], 2) for s_ in ref["segments"]][:2]
+    got = m.transcribe_batch(clips, **kw)
+    report, identical = [], 0
+    for a, g in zip(clips, got):
+        ref = wo.transcribe(pw, dims, a, **kw)
+        gs, rs = g["segments"], ref["segments"]
+        gt = [t for s_ in gs for t in s_["tokens"]]
+        rt = [t for s_ in rs for t in s_["tokens"]]
+        assert g["language"] == "ja" and all(s_["end"] >= s_["start"] for s_ in gs)
+        if gt == rt:
+            identical += 1
+            assert len(gs) == len(rs)
+            for x, y in zip(gs, rs):
+                assert x["seek"] == y["seek"] and abs(x["start"] - y["start"]) < 1e-6 and abs(x["end"] - y["end"]) < 1e-6
+                assert abs(x["avg_logprob"] - y["avg_logprob"]) <= 2e-2 and abs(x["no_speech_prob"] - y["no_speech_prob"]) <= 1e-3
+                assert abs(x["compression_ratio"] - y["compression_ratio"]) <= 1e-6
+            report.append({"identical": True, "tokens": len(gt)})
+            continue
+        # first divergence: find the window (seek) it falls in, decode that one window on both sides (mel + encoder + decoder),
+        # and require the first differing step to be a near-tie on the oracle's own logits
+        div = next(i for i in range(max(len(gt), len(rt))) if i >= min(len(gt), len(rt)) or gt[i] != rt[i])
+        acc, seek = 0, rs[-1]["seek"]
+        for s_ in rs:
+            if acc + len(s_["tokens"]) > div:
+                seek = s_["seek"]
+                break
+            acc += len(s_["tokens"])
+        arr = [np.asarray(a, np.float32)]
+        mels = m._clip_mels(arr, [len(a) // 160])
+        size = min(wo.N_FRAMES, len(a) // 160 - seek)
+        g_one = m.decode_features(m.encode(m._gather_windows(mels, [0], [seek], [size])), language="ja", max_initial_timestamp=0.0)[0]
+        mel = wo.log_mel_spectrogram(a, dims.n_mels, padding=wo.N_SAMPLES)
+        win = wo.pad_or_trim(mel[:, seek: seek + wo.N_FRAMES][:, :size], wo.N_FRAMES)
+        one = wo.decode(pw, dims, win[None], wo.DecodingOptions(language="ja", max_initial_timestamp=0.0), True)[0]
+        j = next((i for i in range(min(len(g_one.tokens), len(one.tokens))) if g_one.tokens[i] != one.tokens[i]), min(len(g_one.tokens), len(one.tokens)))
+        margin = one.margins[j] if j < len(one.margins) else None
+        report.append({"identical": False, "div": div, "seek": seek, "window_step": j, "oracle_margin": margin})
+        assert margin is not None and margin <= 16 * P.fp16_quantum(32.0), report[-1]
     (diag_dir / "transcribe_tiny.json").write_text(json.dumps(report))
+    assert identical >= len(clips) - 1, report
+
+
+def test_hf_greedy_fixture_on_gpu(tiny):
+    """The committed HF fixture (tests/golden/hf_tiny_greedy.npz: HF WhisperForConditionalGeneration, fp32, unfiltered greedy) run
+    on the device: HF-semantics mel -> encoder -> teacher-forced decode; step logits within fp16 distance of HF's."""
+    dims, w, m, pw = tiny
+    z = np.load(G / "hf_tiny_greedy.npz")
+    a = speech_shaped_audio(12.0, 1001)
+    audio = torch.zeros(1, 480000)
+    audio[0, : len(a)] = torch.from_numpy(a)
+    mel = m.log_mel(audio.cuda(), torch.tensor([480000], dtype=torch.int32).cuda(), n_frames=3000, layout="time", reflect_total=480000)
+    xa = m.encode(mel)
+    enc = xa[0].float().cpu().numpy()
+    assert np.abs(enc[::50, ::16] - z["enc"]).max() <= 1e-2 * np.abs(z["enc"]).max() + 1e-2
+    ids = z["ids"].tolist()
+    # HF prefix <sot><ja><transcribe><notimestamps>; suppress nothing that HF did not suppress: compare raw logits, force HF's ids
+    res, tr = m.decode_trace(xa, forced_tokens=[ids[4:]], language="ja", without_timestamps=True, sample_len=len(ids) - 4)
+    n0 = tr["n_initial"]
+    for step in range(len(ids) - 4):
+        got = tr["logits"][n0 - 1 + step, 0].numpy()[::97]
+        assert np.abs(got - z["logits"][step]).max() <= 0.02 * np.abs(z["logits"][step]).max() + 0.05, step
 
 
 def test_temperature_fallback_and_sampling(tiny, clips):
     """T > 0 draws from Categorical(logits / T): different seeds give different valid sequences, T -> 0+ reproduces
     greedy, and the fallback ladder re-decodes exactly the windows that fail the thresholds."""
-    dims, w, m = tiny
-    mel_tm = _gpu_mel(m, clips[:3])
-    xa = m.encode(mel_tm)
+    dims, w, m, pw = tiny
+    xa = m.encode(P.gpu_mel(m, clips[:3]))
     greedy = m.decode_features(xa, language="ja", max_initial_timestamp=0.0, temperature=0.0)
     cold = m.decode_features(xa, language="ja", max_initial_timestamp=0.0, temperature=1e-4, seed=1)
     assert [r.tokens[:6] for r in cold] == [r.tokens[:6] for r in greedy]  # exact ties (fp16 logits) may break differently later on
@@ -154,45 +198,67 @@ def test_temperature_fallback_and_sampling(tiny, clips):
                              compression_ratio_threshold=None, condition_on_previous_text=False, max_initial_timestamp=0.0, best_of=2)
     assert all(s_["temperature"] == 1.0 for o in out for s_ in o["segments"])
     assert m.stats["device_passes"] - p0 >= 1 + 2 + 2                # T=0 once, then best_of=2 at each T > 0
-    p0 = m.stats["device_passes"]
     out = m.transcribe_batch(clips[:2], language="ja", temperature=(0.0, 0.5), logprob_threshold=-50.0, no_speech_threshold=None,
                              compression_ratio_threshold=None, condition_on_previous_text=False, max_initial_timestamp=0.0)
     assert all(s_["temperature"] == 0.0 for o in out for s_ in o["segments"])
 
 
+def test_suppress_none_still_masks_specials(tiny, clips):
+    """upstream _get_suppress_tokens: suppress_tokens=None / "" / [] still suppress sot / task / no_speech ids."""
+    dims, w, m, pw = tiny
+    xa = m.encode(P.gpu_mel(m, clips[:2]))
+    tok = M.Tokens(dims.n_vocab, "ja")
+    specials = {tok.transcribe, tok.translate, tok.sot, tok.sot_prev, tok.sot_lm, tok.no_speech}
+    for spec in (None, "", []):
+        rep = P.decode_parity(m, w, dims, xa, prepared=pw, language="ja", without_timestamps=True, suppress_tokens=spec, sample_len=40)
+        assert rep["ok"], rep["failures"]
+        assert not (specials & {t for row in rep["tokens"] for t in row})
+
+
 @pytest.mark.parametrize("beam,patience", [(1, None), (2, 1.2), (3, 1.5)])
 def test_beam_search_matches_oracle(tiny, clips, diag_dir, beam, patience):
-    """BeamSearchDecoder on the device (ancestry-table KV cache, per-window candidate ranking) against the oracle's restatement,
-    short horizon so that the oracle finishes in seconds.  Scores of competing hypotheses can be closer than fp16 logit noise, so
-    identity is required for most windows and a close score for all of them; beam_size 1 must reproduce the greedy decode."""
-    dims, w, m = tiny
-    xa = m.encode(_gpu_mel(m, clips))
-    kw = dict(language="ja", without_timestamps=True, sample_len=12)
+    """BeamSearchDecoder on the device (ancestry-table KV cache, per-window candidate ranking) against the oracle's restatement.
+    Competing hypotheses can score closer than fp16 logit noise, so identity is required for most windows and a close score for
+    all of them; beam_size 1 must reproduce the greedy decode."""
+    dims, w, m, pw = tiny
+    xa = m.encode(P.gpu_mel(m, clips))
+    kw = dict(language="ja", without_timestamps=True, sample_len=32)
     res = m.decode_features(xa, beam_size=beam, patience=patience, **kw)
     if beam == 1:
         greedy = m.decode_features(xa, **kw)
         assert [r.tokens for r in res] == [r.tokens for r in greedy]
         assert [r.sum_logprob for r in res] == pytest.approx([r.sum_logprob for r in greedy], abs=1e-3)
         assert [r.no_speech_prob for r in res] == pytest.approx([r.no_speech_prob for r in greedy], abs=1e-6)
-    opts = wo.DecodingOptions(language="ja", without_timestamps=True, sample_len=12, beam_size=beam, patience=patience)
-    ref = wo.decode(w, dims, None, opts, True, audio_features=xa.float().cpu())
+    opts = wo.DecodingOptions(beam_size=beam, patience=patience, **kw)
+    ref = wo.decode(pw, dims, None, opts, True, audio_features=xa.float().cpu())
     report = [{"gpu": g.tokens, "oracle": r.tokens, "gpu_sum": g.sum_logprob, "oracle_sum": r.sum_logprob} for g, r in zip(res, ref)]
     (diag_dir / f"beam_tiny_{beam}.json").write_text(json.dumps(report, indent=1))
     same = sum(g.tokens == r.tokens for g, r in zip(res, ref))
     for g, r in zip(res, ref):
-        assert abs(g.no_speech_prob - r.no_speech_prob) <= 1e-3 + 0.02 * r.no_speech_prob
+        assert abs(g.no_speech_prob - r.no_speech_prob) <= 1e-3 + 0.03 * r.no_speech_prob
         assert abs(g.avg_logprob - r.avg_logprob) <= 0.1, report  # a different pick among near-equal hypotheses scores about the same
         if g.tokens == r.tokens:
-            assert abs(g.sum_logprob - r.sum_logprob) <= 0.15
+            assert abs(g.sum_logprob - r.sum_logprob) <= 0.02 * (len(g.tokens) + 1)
     assert same >= len(ref) - 1, report
-    # again: bit-reproducible
-    res2 = m.decode_features(xa, beam_size=beam, patience=patience, **kw)
+    res2 = m.decode_features(xa, beam_size=beam, patience=patience, **kw)   # bit-reproducible
     assert [r.tokens for r in res2] == [r.tokens for r in res]
 
 
 def test_transcribe_with_beam_size_runs_the_beam_decoder(tiny, clips):
-    dims, w, m = tiny
+    dims, w, m, pw = tiny
     s0 = m.stats["device_passes"]
     out = m.transcribe_batch(clips[:2], language="ja", temperature=0.0, beam_size=2, patience=1.2, condition_on_previous_text=False,
                              without_timestamps=True, sample_len=8)
     assert len(out) == 2 and all("segments" in o for o in out) and m.stats["device_passes"] > s0
+
+
+def test_upstream_transcribe_keywords_are_accepted(tiny, clips):
+    """Every keyword of upstream whisper.transcribe() is accepted by name (the reference's config.template.json ships
+    hallucination_silence_threshold); names upstream would reject still raise TypeError."""
+    dims, w, m, pw = tiny
+    out = m.transcribe(clips[2], language="ja", temperature=0.0, hallucination_silence_threshold=2.0, clip_timestamps="0",
+                       prepend_punctuations="\"'“¿([{-", append_punctuations="\"'.。,，!！?？:：”)]}、", condition_on_previous_text=False,
+                       sample_len=8, fp16=True, verbose=None)
+    assert "segments" in out
+    with pytest.raises(TypeError):
+        m.transcribe(clips[2], language="ja", no_such_option=1)

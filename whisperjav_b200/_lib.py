@@ -48,6 +48,7 @@ _SIGS = {
                                  C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "wjb_encoder_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "wjb_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wjb_encoder_set_tap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "wjb_cross_kv_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "wjb_cross_kv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "wjb_decode_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),

@@ -106,7 +106,7 @@ class B200WhisperASR:
 
     def _minimal_whisper_params(self) -> Dict:
         return {"task": self.whisper_params.get("task", "transcribe"), "language": self.whisper_params.get("language", "ja"),
-                "temperature": 0.0, "fp16": True, "verbose": None}
+                "temperature": 0.0, "beam_size": 3, "fp16": True, "verbose": None}  # whisper_pro_asr.py:446-454
 
     def _run_batch(self, chunks: List[np.ndarray]) -> List[Optional[dict]]:
         params = self._prepare_whisper_params()
@@ -115,8 +115,10 @@ class B200WhisperASR:
             return self.whisper_model.transcribe_batch(chunks, **params)
         except Exception as e:  # retry once with minimal params, then give up on the batch (whisper_pro_asr.py:432-444)
             logger.error(f"B200 transcription failed: {e}", exc_info=True)
+            minimal = self._minimal_whisper_params()
             try:
-                return self.whisper_model.transcribe_batch(chunks, **self._minimal_whisper_params())
+                logger.warning(f"Retrying transcription with minimal parameters: {minimal}")
+                return self.whisper_model.transcribe_batch(chunks, **minimal)
             except Exception as e2:
                 logger.error(f"Original error: {e}; fallback error: {e2}")
                 return [None] * len(chunks)

@@ -212,6 +212,8 @@ struct wjb_model {
     int32_t* trace_sampled = nullptr;
     const int32_t* trace_forced = nullptr;
     const void *g_trace_logits = nullptr, *g_trace_sampled = nullptr, *g_trace_forced = nullptr;
+    void* enc_tap = nullptr;  // test hook (wjb_encoder_set_tap): residual stream after block index k * enc_tap_every - 1
+    int enc_tap_every = 0;
     const __half* h16(const std::string& name) const { return reinterpret_cast<const __half*>(blob + L.off(name)); }
     const float* f32(const std::string& name) const { return reinterpret_cast<const float*>(blob + L.off(name)); }
 };
@@ -429,8 +431,21 @@ int wjb_encoder_forward(wjb_model* m, const void* mel_tm, int batch, void* out, 
         if (int e = ln(w.x, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"), w.h)) return e;
         if (int e = linear(w.h, n, m->h16(p + "fc1.w"), m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, GEMM_GELU)) return e;
         if (int e = linear(w.mlp, 4 * n, m->h16(p + "fc2.w"), m->h16(p + "fc2.b"), w.x, w.x, n, 0)) return e;
+        if (m->enc_tap && m->enc_tap_every > 0 && (i + 1) % m->enc_tap_every == 0) {
+            const size_t bytes = (size_t)M * n * 2;
+            cudaError_t ce = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(m->enc_tap) + ((i + 1) / m->enc_tap_every - 1) * bytes, w.x, bytes,
+                                             cudaMemcpyDeviceToDevice, s);
+            if (ce != cudaSuccess) return set_error("encoder tap: %s", cudaGetErrorString(ce));
+        }
     }
     return ln(w.x, m->h16("enc.ln_post.g"), m->h16("enc.ln_post.b"), reinterpret_cast<__half*>(out));
+}
+
+int wjb_encoder_set_tap(wjb_model* m, void* out, int every) {
+    if (!m) return set_error("encoder_set_tap: null model");
+    m->enc_tap = out;
+    m->enc_tap_every = out ? every : 0;
+    return 0;
 }
 
 // ------------------------------------------------------------------ cross K/V

@@ -25,7 +25,7 @@ import torch
 
 from . import _lib
 from .hostlogic import beam_finalize_and_rank
-from .synth import DIMS, Dims, synth_weights
+from .synth import DIMS, Dims, synth_preset, synth_weights
 from .weights import pack_weights
 
 SAMPLE_RATE = 16000
@@ -33,7 +33,19 @@ N_FFT = 400
 HOP_LENGTH = 160
 N_SAMPLES = 480000
 N_FRAMES = 3000
-LANGUAGES = ("en", "zh", "de", "es", "ru", "ko", "fr", "ja", "pt", "tr", "pl", "ca", "nl", "ar", "sv", "it", "id", "hi", "fi", "vi")
+# upstream whisper/tokenizer.py::LANGUAGES, in token-id order (<|en|> = sot + 1, ...); the last entry ("yue") exists only in the
+# 51866-token vocabulary of large-v3 / turbo
+LANGUAGES = ("en", "zh", "de", "es", "ru", "ko", "fr", "ja", "pt", "tr", "pl", "ca", "nl", "ar", "sv", "it", "id", "hi", "fi", "vi",
+             "he", "uk", "el", "ms", "cs", "ro", "da", "hu", "ta", "no", "th", "ur", "hr", "bg", "lt", "la", "mi", "ml", "cy", "sk",
+             "te", "fa", "lv", "bn", "sr", "az", "sl", "kn", "et", "mk", "br", "eu", "is", "hy", "ne", "mn", "bs", "kk", "sq", "sw",
+             "gl", "mr", "pa", "si", "km", "sn", "yo", "so", "af", "oc", "ka", "be", "tg", "sd", "gu", "am", "yi", "lo", "uz", "fo",
+             "ht", "ps", "tk", "nn", "mt", "sa", "lb", "my", "bo", "tl", "mg", "as", "tt", "haw", "ln", "ha", "ba", "jw", "su", "yue")
+# upstream tokenizer.py::TO_LANGUAGE_CODE aliases that reference configs use ("japanese" -> "ja", ...)
+LANGUAGE_ALIASES = {"english": "en", "chinese": "zh", "german": "de", "spanish": "es", "russian": "ru", "korean": "ko", "french": "fr",
+                    "japanese": "ja", "portuguese": "pt", "turkish": "tr", "polish": "pl", "dutch": "nl", "arabic": "ar", "swedish": "sv",
+                    "italian": "it", "indonesian": "id", "hindi": "hi", "finnish": "fi", "vietnamese": "vi", "cantonese": "yue",
+                    "mandarin": "zh", "burmese": "my", "castilian": "es", "flemish": "nl", "haitian": "ht", "moldavian": "ro",
+                    "moldovan": "ro", "sinhalese": "si", "valencian": "ca", "panjabi": "pa", "pushto": "ps", "letzeburgesch": "lb"}
 
 # Non-speech symbol token ids of the multilingual vocabulary (upstream tokenizer.non_speech_tokens;
 # identical to the head of transformers' NON_SPEECH_TOKENS_MULTI).
@@ -72,8 +84,10 @@ class Tokens:
         base = self.sot + 1 + self.num_languages
         self.translate, self.transcribe, self.sot_lm, self.sot_prev = base, base + 1, base + 2, base + 3
         self.no_speech, self.no_timestamps, self.timestamp_begin = base + 4, base + 5, base + 6
-        if language not in LANGUAGES:
-            raise ValueError(f"unsupported language {language!r} (ids are tabulated for {LANGUAGES})")
+        language = LANGUAGE_ALIASES.get(str(language).lower(), str(language).lower())
+        if language not in LANGUAGES[: self.num_languages]:
+            raise ValueError(f"Unsupported language: {language}")
+        self.language = language
         if task not in ("transcribe", "translate"):
             raise ValueError(f"unsupported task {task!r}")
         self.language_token = self.sot + 1 + LANGUAGES.index(language)
@@ -95,6 +109,15 @@ class Tokens:
 
 
 _detok_hook = None
+_warned = set()
+
+
+def _warn_once(key: str, msg: str) -> None:
+    if key not in _warned:
+        _warned.add(key)
+        import logging
+        logging.getLogger("whisperjav_b200").warning(msg)
+
 
 
 def set_detokenizer(fn) -> None:
@@ -197,10 +220,18 @@ class WhisperB200:
                                               _lib.stream_ptr()), "wjb_logmel_f16")
         return out
 
-    def encode(self, mel_tm: torch.Tensor) -> torch.Tensor:
-        """mel_tm fp16 [B, 3002, n_mels] -> audio features fp16 [B, 1500, n_state]."""
+    def encode(self, mel_tm: torch.Tensor, tap_every: int = 0):
+        """mel_tm fp16 [B, 3002, n_mels] -> audio features fp16 [B, 1500, n_state].  ``tap_every`` (parity tests): also return
+        the residual stream after every ``tap_every``-th block, fp16 [n_audio_layer // tap_every, B, 1500, n_state]."""
         B = mel_tm.shape[0]
         d = self.dims
+        if tap_every:
+            taps = torch.empty(d.n_audio_layer // tap_every, B, d.n_audio_ctx, d.n_audio_state, dtype=torch.float16, device=self.device)
+            _lib.check(self.lib.wjb_encoder_set_tap(self._h, _lib.ptr(taps), tap_every), "wjb_encoder_set_tap")
+            try:
+                return self.encode(mel_tm), taps
+            finally:
+                self.lib.wjb_encoder_set_tap(self._h, None, 0)
         assert mel_tm.shape[1] == 2 * d.n_audio_ctx + 2 and mel_tm.shape[2] == d.n_mels and mel_tm.is_contiguous()
         out = torch.empty(B, d.n_audio_ctx, d.n_audio_state, dtype=torch.float16, device=self.device)
         nb = self.lib.wjb_encoder_workspace_bytes(self._h, B)
@@ -215,7 +246,7 @@ class WhisperB200:
                         sample_len: Optional[int] = None, prompt: Optional[Sequence[int]] = None,
                         prefix: Optional[Sequence[int]] = None, temperature: float = 0.0, seed: int = 0,
                         beam_size: Optional[int] = None, patience: Optional[float] = None,
-                        length_penalty: Optional[float] = None) -> List[DecodingResult]:
+                        length_penalty: Optional[float] = None, _trace: Optional[dict] = None) -> List[DecodingResult]:
         """Decode B windows (upstream DecodingTask.run) in one device-resident loop: GreedyDecoder (argmax at T == 0,
         Categorical(logits / T) otherwise) or, with ``beam_size``, BeamSearchDecoder at T == 0."""
         d = self.dims
@@ -225,9 +256,8 @@ class WhisperB200:
         sample_len = sample_len or n_ctx // 2
         initial = tok.sot_sequence(without_timestamps)
         if prefix:
-            pfx = list(prefix)
             max_prefix_len = n_ctx // 2 - sample_len
-            initial = initial + (pfx[-max_prefix_len:] if max_prefix_len > 0 else [])
+            initial = initial + list(prefix)[-max_prefix_len:]  # upstream slices unconditionally ([-0:] keeps everything)
         if prompt:
             initial = [tok.sot_prev] + list(prompt)[-(n_ctx // 2 - 1):] + initial
         n_initial = len(initial)
@@ -245,13 +275,12 @@ class WhisperB200:
         opts.tokens_stride, opts.check_every = stride, 8
         opts.temperature, opts.seed = float(temperature), int(seed) & 0xFFFFFFFF
 
-        key = ("mask", hash(str(suppress_tokens)), language, task)
+        # upstream _get_suppress_tokens: None / "" / [] still suppress the task and sot-family specials and no_speech
+        key = ("mask", str(suppress_tokens), language, task)
         mask = self._bufs.get(key)
-        if suppress_tokens is None or suppress_tokens == "" or suppress_tokens == []:
-            mask = None
-        elif mask is None:
+        if mask is None:
             mk = torch.zeros(d.n_vocab, dtype=torch.uint8)
-            mk[tok.suppress_list(suppress_tokens)] = 1
+            mk[tok.suppress_list(suppress_tokens if suppress_tokens not in (None, "") else [])] = 1
             mask = mk.to(self.device)
             self._bufs[key] = mask
         if beam_size:
@@ -272,9 +301,30 @@ class WhisperB200:
             tokens.zero_()
             tokens[:, :n_initial] = torch.tensor(initial, dtype=torch.int32, device=self.device)
             steps = C.c_int(0)
-            _lib.check(self.lib.wjb_decode_greedy(self._h, _lib.ptr(kv), B, C.byref(opts), _lib.ptr(mask), _lib.ptr(tokens),
-                                                 _lib.ptr(slp), _lib.ptr(nsp), _lib.ptr(olen), _lib.ptr(ws), ws_bytes,
-                                                 C.byref(steps), _lib.stream_ptr()), "wjb_decode_greedy")
+            if _trace is not None:  # parity-test hook: per-step raw logits, the device's own picks, optional teacher forcing
+                ls = self.lib.wjb_decode_logits_stride(self._h)
+                t_logits = torch.zeros(n_initial - 1 + sample_len, B, ls, dtype=torch.float16, device=self.device)
+                t_sampled = torch.full((B, stride), -1, dtype=torch.int32, device=self.device)
+                t_forced = None
+                if _trace.get("forced") is not None:
+                    ft = torch.full((B, stride), tok.eot, dtype=torch.int32)
+                    for b, seq in enumerate(_trace["forced"]):
+                        seq = list(seq)[: stride - n_initial]
+                        ft[b, n_initial: n_initial + len(seq)] = torch.tensor(seq, dtype=torch.int32)
+                    t_forced = ft.to(self.device)
+                _lib.check(self.lib.wjb_decode_set_trace(self._h, _lib.ptr(t_logits), t_logits.numel() * 2, _lib.ptr(t_sampled),
+                                                        _lib.ptr(t_forced)), "wjb_decode_set_trace")
+            try:
+                _lib.check(self.lib.wjb_decode_greedy(self._h, _lib.ptr(kv), B, C.byref(opts), _lib.ptr(mask), _lib.ptr(tokens),
+                                                     _lib.ptr(slp), _lib.ptr(nsp), _lib.ptr(olen), _lib.ptr(ws), ws_bytes,
+                                                     C.byref(steps), _lib.stream_ptr()), "wjb_decode_greedy")
+            finally:
+                if _trace is not None:
+                    self.lib.wjb_decode_set_trace(self._h, None, 0, None, None)
+            if _trace is not None:
+                _trace["logits"] = t_logits[: steps.value, :, : d.n_vocab].float().cpu()  # [steps_run][B][V]
+                _trace["sampled"] = t_sampled.cpu().numpy()
+                _trace["n_initial"], _trace["steps"] = n_initial, steps.value
             host = out[: B * stride + 3 * B].cpu()  # the one device->host read of the decode
         self.stats["decode_steps"] += steps.value
         self.stats["windows"] += B
@@ -292,6 +342,15 @@ class WhisperB200:
                                           compression_ratio=compression_ratio(text) if text else 0.0, language=language,
                                           sum_logprob=float(h_slp[b])))
         return results
+
+    def decode_trace(self, xa: torch.Tensor, forced_tokens: Optional[Sequence[Sequence[int]]] = None, **kw):
+        """Parity-test entry: greedy decode of ``xa`` that also returns the raw step logits.  Returns (results, trace) with
+        trace["logits"] fp32 [steps][B][n_vocab] (row ``n_initial - 1 + i`` holds the logits the i-th sampled token was drawn
+        from), trace["sampled"] the ids the device picked at every position, trace["n_initial"].  With ``forced_tokens`` the
+        device is fed those ids instead of its own picks (teacher forcing)."""
+        trace = {"forced": forced_tokens}
+        res = self.decode_features(xa, _trace=trace, **kw)
+        return res, trace
 
     def _decode_beam(self, xa, opts, mask, initial, tok, beam: int, patience, length_penalty, language) -> List[DecodingResult]:
         """upstream decoding.py::DecodingTask.run with BeamSearchDecoder: the device runs update() for every step
@@ -357,12 +416,24 @@ class WhisperB200:
                          compression_ratio_threshold: Optional[float] = 2.4, logprob_threshold: Optional[float] = -1.0,
                          no_speech_threshold: Optional[float] = 0.6, condition_on_previous_text: bool = True,
                          initial_prompt: Optional[Sequence[int]] = None, word_timestamps: bool = False,
-                         carry_initial_prompt: bool = False, pinned_audio: Optional[torch.Tensor] = None,
+                         carry_initial_prompt: bool = False, prepend_punctuations: str = "\"'“¿([{-",
+                         append_punctuations: str = "\"'.。,，!！?？:：”)]}、", clip_timestamps: Union[str, List[float]] = "0",
+                         hallucination_silence_threshold: Optional[float] = None, pinned_audio: Optional[torch.Tensor] = None,
                          **decode_options) -> List[dict]:
-        """Independent clips (each: fp32 mono 16 kHz) -> one upstream-shaped result dict per clip."""
+        """Independent clips (each: fp32 mono 16 kHz) -> one upstream-shaped result dict per clip.  Every keyword of upstream
+        ``whisper.transcribe()`` is accepted by name; names upstream would reject raise TypeError as ``DecodingOptions(**kw)`` does."""
         unknown = set(decode_options) - _DECODE_KEYS
         if unknown:  # upstream: DecodingOptions(**kwargs) raises TypeError
             raise TypeError(f"transcribe() got unexpected keyword arguments {sorted(unknown)}")
+        if clip_timestamps not in ("0", [0], [0.0], 0, None, []):
+            _warn_once("clip_timestamps", "clip_timestamps other than the default \"0\" is not implemented: whole clips are transcribed")
+        if hallucination_silence_threshold is not None and not word_timestamps:
+            pass  # upstream only consults it when word_timestamps=True
+        elif hallucination_silence_threshold is not None:
+            _warn_once("hst", "hallucination_silence_threshold is accepted but the silence-skipping heuristic is not implemented")
+        if decode_options.get("language") is None:
+            _warn_once("lang", "language=None: upstream would run language detection; this backend decodes as 'ja' (the reference's "
+                               "configured language, whisper_pro_asr.py:36)")
         language = decode_options.pop("language", None) or "ja"
         task = decode_options.pop("task", "transcribe")
         decode_options.pop("fp16", None)
@@ -576,7 +647,7 @@ class WhisperB200:
 
 
 def load_model(name: str = "large-v3", device: Union[str, torch.device] = "cuda", state_dict: Optional[dict] = None,
-               seed: int = 11, max_batch: int = 64) -> WhisperB200:
+               seed: Optional[int] = None, max_batch: int = 64) -> WhisperB200:
     """``whisper.load_model(name, device)`` stand-in (whisper_pro_asr.py:182).  With no checkpoint
     reachable (no network on either box) ``state_dict=None`` builds the seeded synthetic weights of
     that architecture; pass a real openai- or HF-named ``state_dict`` to run real weights."""
@@ -584,5 +655,8 @@ def load_model(name: str = "large-v3", device: Union[str, torch.device] = "cuda"
         raise RuntimeError(f"Model {name} not found; available models = {sorted(DIMS)}")
     dims = DIMS[name]
     if state_dict is None:
-        state_dict = synth_weights(dims, seed=seed)
+        kw = synth_preset(name)
+        if seed is not None:
+            kw["seed"] = seed
+        state_dict = synth_weights(dims, **kw)
     return WhisperB200(dims, state_dict, device=device, max_batch=max_batch)

@@ -38,9 +38,12 @@ DIMS = {
     "base": Dims(80, 1500, 512, 8, 6, 51865, 448, 512, 8, 6),
     "small": Dims(80, 1500, 768, 12, 12, 51865, 448, 768, 12, 12),
     "medium": Dims(80, 1500, 1024, 16, 24, 51865, 448, 1024, 16, 24),
+    "large-v1": Dims(80, 1500, 1280, 20, 32, 51865, 448, 1280, 20, 32),
     "large-v2": Dims(80, 1500, 1280, 20, 32, 51865, 448, 1280, 20, 32),
-    "large": Dims(80, 1500, 1280, 20, 32, 51865, 448, 1280, 20, 32),
     "large-v3": Dims(128, 1500, 1280, 20, 32, 51866, 448, 1280, 20, 32),
+    "large": Dims(128, 1500, 1280, 20, 32, 51866, 448, 1280, 20, 32),  # upstream alias of large-v3
+    "large-v3-turbo": Dims(128, 1500, 1280, 20, 32, 51866, 448, 1280, 20, 4),
+    "turbo": Dims(128, 1500, 1280, 20, 32, 51866, 448, 1280, 20, 4),
 }
 
 EOT = 50257
@@ -53,11 +56,40 @@ def _sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> to
     return torch.cat([torch.sin(t), torch.cos(t)], dim=1)
 
 
+# Per-architecture generator settings used by load_model(), bench.py and the tests: seeds / EOT boosts picked (with
+# scripts/synth_stats.py, CPU oracle) so that greedy sequences end at varied lengths in both timestamp modes.
+SYNTH_PRESETS = {
+    "tiny": {"seed": 5},
+    "large-v3": {"seed": 11, "eot_boost": 2.3},
+}
+
+
+def synth_preset(name: str) -> dict:
+    return dict(SYNTH_PRESETS.get(name, {"seed": 11}))
+
+
 def synth_weights(dims: Dims, seed: int = 11, dtype=torch.float16, eot_boost: float = 1.8,
-                  logit_std: float = 3.0, attn_logit_std: float = 10.0, res_gain: float = None,
-                  cross_gain: float = 0.3, bias_std: float = 0.02) -> Dict[str, torch.Tensor]:
+                  logit_std: float = 7.0, attn_logit_std: float = 8.0, res_gain: float = None,
+                  cross_gain: float = 0.4, bias_std: float = 0.02, emb_norm_sigma: float = 0.0,
+                  eot_drift: float = 0.0, eot_t0: float = 100.0,
+                  enc_attn_logit_std: float = 2.0, cross_attn_logit_std: float = 8.0,
+                  emb_scale: float = 1.0) -> Dict[str, torch.Tensor]:
     """Seeded weights in openai-whisper ``state_dict`` naming.  Stored in ``dtype`` (fp16:
-    what the reference's ``fp16=True`` run holds after ``model.half()``)."""
+    what the reference's ``fp16=True`` run holds after ``model.half()``).
+
+    The defaults are tuned on the CPU oracle (scripts/synth_stats.py; asserted in tests/test_oracle_synth.py) for what a
+    parity test needs from a random-init model:
+    * decoder self- and cross-attention are sharp (score std 8) so the hidden state, and with it the arg-max, moves from step
+      to step and depends on which audio frames the step attends to (a soft cross-attention adds the same vector every step:
+      repeats, no EOT); encoder self-attention is soft (2) -- sharp softmaxes amplify fp16 rounding differences (encoder
+      fp16-vs-fp32 relative difference 7.6e-3 at std 10, 7e-4 at std 2) without adding anything the test needs;
+    * embedding rows are small against the block outputs (a tied embedding's own logit grows with |row|^2 / rms(residual):
+      large rows make the model repeat its input token) and the final LayerNorm gain sets the logit spread to
+      ``logit_std`` = 7: top logits around 30, avg_logprob around -0.6 (above the reference's logprob_threshold of -1.0, so the
+      temperature ladder is not permanently triggered), oracle top-2 margins with median about 1.2;
+    * 50 k exchangeable Gaussian logits have a top-2 gap that is exponentially distributed with mean sigma / sqrt(2 ln V):
+      about 6 % of steps have a margin below 0.1 whatever the seed.  A trained model is more decisive than that; a random
+      one cannot be, so the parity tests judge near-ties explicitly (oracle/parity.py) instead of assuming there are none."""
     g = torch.Generator().manual_seed(seed)
     if res_gain is None:
         res_gain = math.sqrt(32.0 / dims.n_text_layer)
@@ -71,10 +103,10 @@ def synth_weights(dims: Dims, seed: int = 11, dtype=torch.float16, eot_boost: fl
         w[prefix + ".weight"] = (1.0 + 0.1 * torch.randn(n, generator=g)).to(dtype)
         w[prefix + ".bias"] = rn(n, std=bias_std)
 
-    def attn(prefix, n, n_head, gain=1.0):
+    def attn(prefix, n, n_head, gain=1.0, logit_std_=None):
         d = n // n_head
         # q.k/sqrt(d) with unit-variance inputs has std  sq*sk*n*sqrt(d)/sqrt(d) = sq*sk*n
-        s_qk = math.sqrt(attn_logit_std / n)
+        s_qk = math.sqrt((logit_std_ or attn_logit_std) / n)
         w[prefix + ".query.weight"] = rn(n, n, std=s_qk)
         w[prefix + ".query.bias"] = rn(n, std=bias_std)
         w[prefix + ".key.weight"] = rn(n, n, std=s_qk)
@@ -98,25 +130,45 @@ def synth_weights(dims: Dims, seed: int = 11, dtype=torch.float16, eot_boost: fl
     for i in range(dims.n_audio_layer):
         p = f"encoder.blocks.{i}"
         ln(p + ".attn_ln", n)
-        attn(p + ".attn", n, dims.n_audio_head)
+        attn(p + ".attn", n, dims.n_audio_head, logit_std_=enc_attn_logit_std)
         ln(p + ".mlp_ln", n)
         mlp(p + ".mlp", n)
     ln("encoder.ln_post", n)
 
     n = dims.n_text_state
-    emb = torch.randn(dims.n_vocab, n, generator=g) * (logit_std / math.sqrt(n))
+    # typical |embedding row| = emb_scale; the final LayerNorm gain brings the logit spread to logit_std (tied embeddings: a
+    # row's own logit grows with |row|^2 / rms(residual), so rows are kept small against the block outputs and the scale of
+    # the logits is set on the way out instead)
+    e_scale = emb_scale if emb_scale else logit_std
+    emb = torch.randn(dims.n_vocab, n, generator=g) * (e_scale / math.sqrt(n))
+    if emb_norm_sigma > 0:
+        # Zipf-like vocabulary: row norms are log-normal, so a few hundred "frequent" ids carry most of the arg-max mass and the
+        # top-2 margin of a step is heavier-tailed than that of 50 k exchangeable Gaussians (scripts/synth_stats.py)
+        norms = torch.exp(emb_norm_sigma * torch.randn(dims.n_vocab, generator=g))
+        norms = norms / norms.pow(2).mean().sqrt()
+        norms[EOT] = 1.0
+        emb = emb * norms[:, None]
     emb[EOT] *= eot_boost
     w["decoder.token_embedding.weight"] = emb.to(dtype)
-    w["decoder.positional_embedding"] = rn(dims.n_text_ctx, n, std=0.5 * logit_std / math.sqrt(n))
+    pos = torch.randn(dims.n_text_ctx, n, generator=g) * (0.5 * e_scale / math.sqrt(n))
+    if eot_drift != 0:
+        # the EOT logit drifts upwards with the position, so that sequences end at audio-dependent but bounded lengths
+        e_hat = emb[EOT] / emb[EOT].norm()
+        t = torch.arange(dims.n_text_ctx, dtype=torch.float32)
+        pos = pos + (eot_drift * e_scale * (t - eot_t0) / (dims.n_text_ctx / 2))[:, None] * e_hat[None, :]
+    w["decoder.positional_embedding"] = pos.to(dtype)
     for i in range(dims.n_text_layer):
         p = f"decoder.blocks.{i}"
         ln(p + ".attn_ln", n)
         attn(p + ".attn", n, dims.n_text_head)
         ln(p + ".cross_attn_ln", n)
-        attn(p + ".cross_attn", n, dims.n_text_head, gain=cross_gain)
+        attn(p + ".cross_attn", n, dims.n_text_head, gain=cross_gain, logit_std_=cross_attn_logit_std)
         ln(p + ".mlp_ln", n)
         mlp(p + ".mlp", n)
     ln("decoder.ln", n)
+    if emb_scale:
+        w["decoder.ln.weight"] = (w["decoder.ln.weight"].float() * (logit_std / e_scale)).to(dtype)
+        w["decoder.ln.bias"] = (w["decoder.ln.bias"].float() * (logit_std / e_scale)).to(dtype)
     return w
 
 
