@@ -60,7 +60,7 @@ def _sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> to
 # scripts/synth_stats.py, CPU oracle) so that greedy sequences end at varied lengths in both timestamp modes.
 SYNTH_PRESETS = {
     "tiny": {"seed": 5},
-    "large-v3": {"seed": 11, "eot_boost": 2.3},
+    "large-v3": {"seed": 11, "eot_boost": 2.8, "attn_logit_std": 10.0, "cross_attn_logit_std": 12.0, "cross_gain": 0.25},
 }
 
 
@@ -235,3 +235,19 @@ def speech_shaped_audio(seconds: float, seed: int, sr: int = 16000, duty: float 
     out = np.clip(out, -1.0, 1.0)
     q = np.round(out * 32767.0).astype(np.int16)  # the WAV hand-off is PCM16
     return (q.astype(np.float32) / 32768.0).astype(np.float32)
+
+
+def speech_shaped_stream(seconds: float, seed: int, n_base: int = 40, clip_s: float = 30.0, sr: int = 16000) -> np.ndarray:
+    """A long "stream" (BASELINE configs 3 / 4: 2 h) assembled from ``n_base`` distinct speech-shaped clips drawn in a seeded
+    order (generating two hours sample by sample would take minutes of host time per stream and add nothing)."""
+    rng = np.random.default_rng(seed)
+    base = [speech_shaped_audio(clip_s, 100000 + 131 * seed + i, sr) for i in range(n_base)]
+    n = int(round(seconds * sr))
+    out = np.empty(n, dtype=np.float32)
+    t = 0
+    while t < n:
+        c = base[int(rng.integers(n_base))]
+        m = min(len(c), n - t)
+        out[t: t + m] = c[:m]
+        t += m
+    return out
