@@ -122,6 +122,27 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
 int wjb_decode_logits_stride(const wjb_model* m);
 int wjb_decode_set_trace(wjb_model* m, void* logits_out, size_t logits_out_bytes, int32_t* sampled_out, const int32_t* forced_tokens);
 
+/* ---- word-level timestamps (openai-whisper timing.py::find_alignment; `word_timestamps=True` in every reference preset,
+ * config/components/asr/openai_whisper.py:213,247,281) -------------------------------------------------------------------
+ * Step 1, the teacher-forced pass: with wjb_decode_set_align set, a wjb_decode_greedy run over tokens = [sot sequence,
+ * <|notimestamps|>, text tokens, <|endoftext|>] (forced through wjb_decode_set_trace, n_initial = len(sot sequence) + 1,
+ * sample_len = max n_tokens - n_initial + 1) feeds every row its n_tokens[b] tokens (no EOT latch) and records
+ *   qk_out          fp16 [B][n_sel][n_steps][n_audio_ctx]: the scaled cross-attention scores q.k / sqrt(64) of every position, for
+ *                   the alignment heads = every head of layers n_text_layer / 2 .. (upstream's default `alignment_heads`);
+ *                   n_sel = (n_text_layer - n_text_layer / 2) * n_text_head, n_steps >= the run's step count;
+ *   token_prob_out  fp32 [B][tokens_stride]: softmax(logits[: eot])[token fed at position p] (timing.py `text_token_probs`).
+ * Step 2, wjb_align_dtw: softmax over the first n_frames2[b] frames, standardisation over the n_tokens[b] token rows, median
+ * filter (medfilt_width 7, or 1 = off), mean over the heads -> matrix fp32 [B][n_steps][n_audio_ctx]; DTW over -matrix rows
+ * row_begin[b] .. row_begin[b] + n_rows[b] - 1 -> jump_frames int32 [B][n_steps]: for DTW row i the first frame of its path
+ * segment (timing.py `time_indices[jumps]`).  All int32 arrays are device memory.  Word grouping and the segment adjustments
+ * are host logic (whisperjav_b200/timing.py). */
+size_t wjb_align_qk_bytes(const wjb_model* m, int batch, int n_steps);
+int wjb_decode_set_align(wjb_model* m, void* qk_out, int n_steps, const int32_t* n_tokens, float* token_prob_out);
+size_t wjb_align_workspace_bytes(const wjb_model* m, int batch, int n_steps);
+int wjb_align_dtw(wjb_model* m, const void* qk, int batch, int n_steps, const int32_t* n_tokens, const int32_t* row_begin,
+                  const int32_t* n_rows, const int32_t* n_frames2, int medfilt_width, float* matrix, int32_t* jump_frames,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- beam search decode (openai-whisper decoding.py::BeamSearchDecoder at temperature 0; replaces the decode inside
  * whisper_pro_asr.py:433 when the preset sets beam_size, config/components/asr/openai_whisper.py:225-292) -----------------
  * Rows are windows x beams (row = window * beam_size + beam).  The self-attention cache is never permuted: every row carries the

@@ -214,7 +214,7 @@ def _attention(q, k, v, n_head, causal: bool, r, capture: Optional[list] = None)
         mask = torch.full((n_ctx, t_k), float("-inf")).triu_(1 + t_k - n_ctx)
         qk = qk + mask
     if capture is not None:
-        capture.append(qk.float())
+        capture.append(r(qk).float())  # fp16 matmul output under fp16=True, then timing.py's .float()
     w = r(torch.softmax(qk.float(), dim=-1))  # non-SDPA branch: softmax(qk.float()).to(q.dtype)
     out = w @ v
     return r(out.permute(0, 2, 1, 3).flatten(start_dim=2))
@@ -728,9 +728,10 @@ def decode_beam(weights, dims: ModelDimensions, mel: torch.Tensor, options: Deco
 
 # ----------------------------------------------------------------------------- transcribe.py
 def slice_segments(tokens: List[int], tok: SpecialTokens, seek: int, segment_size: int,
-                   result_fields: dict, detok=placeholder_detokenize):
+                   result_fields: dict, detok=placeholder_detokenize, clear: bool = True, info: Optional[dict] = None):
     """The timestamp-token segmentation block of transcribe.py::transcribe.
-    Returns (segments, seek_advance_frames)."""
+    Returns (segments, seek_advance_frames).  ``clear=False`` leaves the "instantaneous or empty -> cleared" pass to the caller
+    (upstream runs it after the word-timestamp block); ``info`` receives ``single_timestamp_ending``."""
     input_stride = 2
     time_precision = input_stride * HOP_LENGTH / SAMPLE_RATE
     time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
@@ -768,20 +769,31 @@ def slice_segments(tokens: List[int], tok: SpecialTokens, seek: int, segment_siz
             duration = last_timestamp_pos * time_precision
         segments.append(new_segment(time_offset, time_offset + duration, tokens))
         advance = segment_size
+    if info is not None:
+        info["single_timestamp_ending"] = single_timestamp_ending
+    if clear:
+        clear_empty_segments(segments)
+    return segments, advance
+
+
+def clear_empty_segments(segments: List[dict]) -> None:
     for seg in segments:
         if seg["start"] == seg["end"] or seg["text"].strip() == "":
             seg["text"] = ""
             seg["tokens"] = []
-    return segments, advance
+            if "words" in seg:
+                seg["words"] = []
 
 
 def transcribe(weights, dims: ModelDimensions, audio: np.ndarray, *, task="transcribe", language="ja",
                temperature=(0.0,), compression_ratio_threshold=2.4, logprob_threshold=-1.0,
-               no_speech_threshold=0.6, condition_on_previous_text=True, sim_fp16=True,
+               no_speech_threshold=0.6, condition_on_previous_text=True, sim_fp16=True, word_timestamps=False,
+               prepend_punctuations="\"'“¿([{-", append_punctuations="\"'.。,，!！?？:：”)]}、",
                **decode_options) -> dict:
-    """transcribe.py::transcribe (word_timestamps=False, clip_timestamps="0", language given).
-    One audio array -> {"text", "segments", "language"}.  Greedy or beam search at t == 0 (see ``decode``)."""
-    decode_options = {k: v for k, v in decode_options.items() if k not in ("verbose", "word_timestamps", "fp16")}
+    """transcribe.py::transcribe (clip_timestamps="0", hallucination_silence_threshold=None, language given).
+    One audio array -> {"text", "segments", "language"}.  Greedy or beam search at t == 0 (see ``decode``); with
+    ``word_timestamps`` the alignment block of timing.py (oracle/timing_oracle.py)."""
+    decode_options = {k: v for k, v in decode_options.items() if k not in ("verbose", "fp16")}
     mel = log_mel_spectrogram(audio, dims.n_mels, padding=N_SAMPLES)
     content_frames = mel.shape[-1] - N_FRAMES
     tok = SpecialTokens(dims.n_vocab, language=language, task=task)
@@ -814,6 +826,7 @@ def transcribe(weights, dims: ModelDimensions, audio: np.ndarray, *, task="trans
     all_tokens: List[int] = []
     all_segments: List[dict] = []
     prompt_reset_since = 0
+    last_speech_timestamp = 0.0
     while seek < content_frames:
         segment_size = min(N_FRAMES, content_frames - seek)
         mel_segment = pad_or_trim(mel[:, seek: seek + segment_size], N_FRAMES)
@@ -829,8 +842,24 @@ def transcribe(weights, dims: ModelDimensions, audio: np.ndarray, *, task="trans
                 continue
         fields = {"temperature": result.temperature, "avg_logprob": result.avg_logprob,
                   "compression_ratio": result.compression_ratio, "no_speech_prob": result.no_speech_prob}
-        current_segments, advance = slice_segments(tokens, tok, seek, segment_size, fields)
+        info: dict = {}
+        current_segments, advance = slice_segments(tokens, tok, seek, segment_size, fields, clear=False, info=info)
+        time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
         seek += advance
+        if word_timestamps:
+            from . import timing_oracle as to
+            xa = encoder_forward(weights, dims, mel_segment[None], sim_fp16)
+            to.add_word_timestamps(weights, dims, current_segments, xa, segment_size, language=language, task=task,
+                                   prepend_punctuations=prepend_punctuations, append_punctuations=append_punctuations,
+                                   last_speech_timestamp=last_speech_timestamp, sim_fp16=sim_fp16)
+            if not info["single_timestamp_ending"]:
+                last_word_end = to.get_end(current_segments)
+                if last_word_end is not None and last_word_end > time_offset:
+                    seek = round(last_word_end * FRAMES_PER_SECOND)
+            last_word_end = to.get_end(current_segments)
+            if last_word_end is not None:
+                last_speech_timestamp = last_word_end
+        clear_empty_segments(current_segments)
         all_segments.extend([{"id": i, **s} for i, s in enumerate(current_segments, start=len(all_segments))])
         all_tokens.extend([t for s in current_segments for t in s["tokens"]])
         if not condition_on_previous_text or result.temperature > 0.5:

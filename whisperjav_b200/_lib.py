@@ -57,6 +57,11 @@ _SIGS = {
                                     C.c_void_p]),
     "wjb_decode_logits_stride": (C.c_int, [C.c_void_p]),
     "wjb_decode_set_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "wjb_align_qk_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "wjb_decode_set_align": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "wjb_align_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "wjb_align_dtw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "wjb_decode_beam": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(BeamBufs), C.POINTER(DecodeOpts), C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_size_t, C.POINTER(C.c_int), C.c_void_p]),
     "wjb_gemm_f16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,

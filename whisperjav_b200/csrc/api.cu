@@ -87,6 +87,7 @@ struct ProfScope {
 
 int logmel_init();
 int vad_init();
+int align_init();
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: run the kernel set-up once for every device a caller uses
 // (a process may hold one model per GPU).  Called at the top of every compute entry point, outside any stream capture.
@@ -102,6 +103,7 @@ int ensure_init() {
     if (int e = sample_init()) return e;
     if (int e = logmel_init()) return e;
     if (int e = vad_init()) return e;
+    if (int e = align_init()) return e;
     if (dev < 64) done_mask |= 1ull << dev;
     return 0;
 }
@@ -212,6 +214,13 @@ struct wjb_model {
     int32_t* trace_sampled = nullptr;
     const int32_t* trace_forced = nullptr;
     const void *g_trace_logits = nullptr, *g_trace_sampled = nullptr, *g_trace_forced = nullptr;
+    // word-timestamp alignment pass (wjb_decode_set_align): cross-attention score capture of the upper half of the layers
+    __half* align_qk = nullptr;
+    int align_steps = 0;
+    const int32_t* align_len = nullptr;
+    float* align_prob = nullptr;
+    const void *g_align_qk = nullptr, *g_align_len = nullptr, *g_align_prob = nullptr;
+    int g_align_steps = 0;
     void* enc_tap = nullptr;  // test hook (wjb_encoder_set_tap): residual stream after block index k * enc_tap_every - 1
     int enc_tap_every = 0;
     const __half* h16(const std::string& name) const { return reinterpret_cast<const __half*>(blob + L.off(name)); }
@@ -531,6 +540,38 @@ int wjb_decode_set_trace(wjb_model* m, void* logits_out, size_t logits_out_bytes
     return 0;
 }
 
+size_t wjb_align_qk_bytes(const wjb_model* m, int batch, int n_steps) {
+    if (!m || batch <= 0 || n_steps <= 0) return 0;
+    const wjb_dims& d = m->d;
+    return (size_t)batch * (d.n_text_layer - d.n_text_layer / 2) * d.n_text_head * n_steps * d.n_audio_ctx * 2;
+}
+
+int wjb_decode_set_align(wjb_model* m, void* qk_out, int n_steps, const int32_t* n_tokens, float* token_prob_out) {
+    if (!m) return set_error("decode_set_align: null model");
+    m->align_qk = reinterpret_cast<__half*>(qk_out);
+    m->align_steps = qk_out ? n_steps : 0;
+    m->align_len = qk_out ? n_tokens : nullptr;
+    m->align_prob = qk_out ? token_prob_out : nullptr;
+    return 0;
+}
+
+size_t wjb_align_workspace_bytes(const wjb_model* m, int batch, int n_steps) {
+    if (!m || batch <= 0 || n_steps <= 0) return 0;
+    const wjb_dims& d = m->d;
+    return align_workspace_bytes(batch, (d.n_text_layer - d.n_text_layer / 2) * d.n_text_head, n_steps, d.n_audio_ctx);
+}
+
+int wjb_align_dtw(wjb_model* m, const void* qk, int batch, int n_steps, const int32_t* n_tokens, const int32_t* row_begin, const int32_t* n_rows,
+                  const int32_t* n_frames2, int medfilt_width, float* matrix, int32_t* jump_frames, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+    if (!m || !qk || !n_tokens || !row_begin || !n_rows || !n_frames2 || !matrix || !jump_frames || !workspace)
+        return set_error("align_dtw: null argument");
+    if (int e = ensure_init()) return e;
+    const wjb_dims& d = m->d;
+    return launch_align(reinterpret_cast<const __half*>(qk), batch, (d.n_text_layer - d.n_text_layer / 2) * d.n_text_head, n_steps, d.n_audio_ctx,
+                        n_tokens, row_begin, n_rows, n_frames2, medfilt_width, matrix, jump_frames, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 // The kernels of one decoder step for B rows on stream s (captured into the step graph).
 static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B, const wjb_decode_opts& o, const uint8_t* suppress_mask,
                        int32_t* tokens, float* slp, float* nsp, int32_t* out_len, cudaStream_t s, const BeamBufs* beam = nullptr) {
@@ -592,7 +633,16 @@ static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B
                                          beam ? beam->anc : nullptr, beam ? beam->anc_parity_stride : 0)) return e;
         if (int e = linear(w.a, n, m->h16(p + "out.w"), n, m->h16(p + "out.b"), w.x, w.x, n, n, 0)) return e;
         if (int e = linear(w.x, n, m->h16(p + "cq.w"), n, m->h16(p + "cq.b"), nullptr, w.q, n, n, 0, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"))) return e;
-        if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv) + i * cross_per_layer, w.a, w.done, B, H, T, s, kv_div))
+        CrossCapture cap;
+        const int sel0 = d.n_text_layer / 2;  // alignment heads: every head of the upper half of the layers (upstream default)
+        if (m->align_qk && !beam && i >= sel0) {
+            cap.base = m->align_qk + (long long)(i - sel0) * H * m->align_steps * T;
+            cap.b_stride = (long long)(d.n_text_layer - sel0) * H * m->align_steps * T;
+            cap.head_stride = (long long)m->align_steps * T;
+            cap.step = &w.ctl->step;
+        }
+        if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv) + i * cross_per_layer, w.a, w.done, B, H, T, s, kv_div,
+                                          cap.base ? &cap : nullptr))
             return e;
         if (int e = linear(w.a, n, m->h16(p + "cout.w"), n, m->h16(p + "cout.b"), w.x, w.x, n, n, 0)) return e;
         if (int e = linear(w.x, n, m->h16(p + "fc1.w"), n, m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, 4 * n, GEMM_GELU, m->h16(p + "ln3.g"), m->h16(p + "ln3.b"))) return e;
@@ -619,6 +669,8 @@ static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B
         p.trace_logits = m->trace_logits;
         p.trace_sampled = m->trace_sampled;
         p.trace_forced = m->trace_forced;
+        p.align_len = m->align_len;
+        p.align_prob = m->align_prob;
         if (int e = launch_sample(w.logits, suppress_mask, tokens, slp, nsp, out_len, w.done, w.ctl, p, s)) return e;
     }
     return launch_advance(w.ctl, s);
@@ -645,6 +697,8 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
     if (o.tokens_stride < o.n_initial + o.sample_len) return set_error("decode: tokens_stride too small");
     DecWs w = dec_ws(d, batch, reinterpret_cast<uint8_t*>(workspace));
     if (w.total > workspace_bytes) return set_error("decode: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    if (m->align_qk && (!m->trace_forced || !m->align_len)) return set_error("decode: the alignment pass needs forced tokens and their lengths");
+    if (m->align_qk && total_steps > m->align_steps) return set_error("decode: alignment capture holds %d steps, the run has %d", m->align_steps, total_steps);
     if (m->trace_logits && m->trace_logits_bytes < (size_t)total_steps * batch * w.logits_stride * 2)
         return set_error("decode: logits trace buffer too small (%zu < %zu)", m->trace_logits_bytes, (size_t)total_steps * batch * w.logits_stride * 2);
 
@@ -667,6 +721,8 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
     const bool hit = m->graph && m->g_kv == cross_kv && m->g_ws == workspace && m->g_B == batch && m->g_mask == suppress_mask &&
                      m->g_tokens == tokens && m->g_slp == sum_logprob && m->g_nsp == no_speech_prob && m->g_len == out_len &&
                      m->g_trace_logits == m->trace_logits && m->g_trace_sampled == m->trace_sampled && m->g_trace_forced == m->trace_forced &&
+                     m->g_align_qk == m->align_qk && m->g_align_len == m->align_len && m->g_align_prob == m->align_prob &&
+                     m->g_align_steps == m->align_steps &&
                      memcmp(&m->g_opts, &okey, sizeof(okey)) == 0;
     if (!hit) {
         if (m->graph) {
@@ -701,6 +757,10 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
         m->g_trace_logits = m->trace_logits;
         m->g_trace_sampled = m->trace_sampled;
         m->g_trace_forced = m->trace_forced;
+        m->g_align_qk = m->align_qk;
+        m->g_align_len = m->align_len;
+        m->g_align_prob = m->align_prob;
+        m->g_align_steps = m->align_steps;
     }
     const int check_every = o.check_every > 0 ? o.check_every : 8;
     int step = 0;

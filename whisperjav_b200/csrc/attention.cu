@@ -436,7 +436,8 @@ constexpr int kCbSmem = cb_smem_bytes(1);
 template <int NQ>
 __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
                                                                              __half* __restrict__ out,
-                                                                             const unsigned char* __restrict__ done, int H, int T, int kv_div) {
+                                                                             const unsigned char* __restrict__ done, int H, int T, int kv_div,
+                                                                             const CrossCapture cap) {
     pdl_prologue();
     const int h = blockIdx.x, b = blockIdx.y;
     const int row0 = b * NQ;  // first query row of this CTA
@@ -548,6 +549,12 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
         __syncthreads();  // stage consumed by everyone (and, after the last K chunk, all scores are in smem)
         if (tid == 0 && c + kCbStages < total) issue(c + kCbStages);
         if (c == nck - 1) {
+            if (NQ == 1 && cap.base) {
+                // word-timestamp alignment pass: the scaled scores q.k / sqrt(d) of this (row, head, position), fp16 as the
+                // reference's fp16 attention matmul returns them (timing.py collects them through forward hooks)
+                __half* dst = cap.base + (long long)b * cap.b_stride + (long long)h * cap.head_stride + (long long)(*cap.step) * T;
+                for (int t = tid; t < T; t += kCrossThreads) dst[t] = __float2half_rn(sc[t]);
+            }
             // softmax over the T scores of every query (V chunks are already streaming into the ring)
 #pragma unroll
             for (int i = 0; i < NQ; ++i) {
@@ -592,9 +599,9 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
 
 template <int NQ>
 static int launch_cross_bulk(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T, int kv_div,
-                             cudaStream_t s) {
+                             cudaStream_t s, const CrossCapture& cap) {
     dim3 grid(H, B / NQ);
-    cudaError_t e = launch_k(attn_dec_cross_bulk_kernel<NQ>, grid, dim3(kCrossThreads), (size_t)cb_smem_bytes(NQ), s, q, kv, out, done, H, T, kv_div);
+    cudaError_t e = launch_k(attn_dec_cross_bulk_kernel<NQ>, grid, dim3(kCrossThreads), (size_t)cb_smem_bytes(NQ), s, q, kv, out, done, H, T, kv_div, cap);
     if (e != cudaSuccess) return set_error("attn_dec_cross_bulk launch: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -611,18 +618,20 @@ int attn_cross_init() {
 }
 
 int launch_attn_dec_cross(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T,
-                          cudaStream_t s, int kv_div) {
+                          cudaStream_t s, int kv_div, const CrossCapture* capture) {
+    const CrossCapture cap = capture ? *capture : CrossCapture{};
+    if (cap.base && kv_div != 1) return set_error("attn_dec_cross: score capture needs one query per window");
     if (kv_div < 1) kv_div = 1;
     if (T > kCrossMaxT) return set_error("attn_dec_cross: T %d > %d", T, kCrossMaxT);
     // beam search: the beams of a window share one pass over its K/V when they fit one CTA
     if (kv_div > 1 && kv_div <= kCbMaxQ && B % kv_div == 0) {
         switch (kv_div) {
-            case 2: return launch_cross_bulk<2>(q, kv, out, done, B, H, T, kv_div, s);
-            case 3: return launch_cross_bulk<3>(q, kv, out, done, B, H, T, kv_div, s);
-            case 4: return launch_cross_bulk<4>(q, kv, out, done, B, H, T, kv_div, s);
+            case 2: return launch_cross_bulk<2>(q, kv, out, done, B, H, T, kv_div, s, cap);
+            case 3: return launch_cross_bulk<3>(q, kv, out, done, B, H, T, kv_div, s, cap);
+            case 4: return launch_cross_bulk<4>(q, kv, out, done, B, H, T, kv_div, s, cap);
         }
     }
-    return launch_cross_bulk<1>(q, kv, out, done, B, H, T, kv_div, s);
+    return launch_cross_bulk<1>(q, kv, out, done, B, H, T, kv_div, s, cap);
 }
 
 }  // namespace wjb

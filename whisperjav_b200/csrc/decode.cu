@@ -369,6 +369,31 @@ sample_kernel(const __half* __restrict__ logits, const unsigned char* __restrict
         if (tid == 0) no_speech_prob[b] = __expf(__half2float(srow[p.no_speech]) - a.v) / s;
     }
     if (!sampling || done[b]) return;
+    if (p.align_len) {
+        // alignment pass: nothing is sampled.  Feed the forced token of the next position, record its probability under the raw
+        // logits restricted to ids < eot (timing.py: logits[:, :eot].softmax), finish the row after its last token was fed.
+        if (cur_len >= p.align_len[b]) {
+            if (tid == 0) {
+                done[b] = 1;
+                out_len[b] = cur_len - n_initial;
+                atomicAdd(&ctl->n_done, 1);
+            }
+            return;
+        }
+        const int tok = p.trace_forced[(long long)b * p.tokens_stride + cur_len];
+        ArgMax a{-INFINITY, 0};
+        for (int v = tid; v < p.eot; v += kSampleThreads) a = amax(a, ArgMax{__half2float(srow[v]), v});
+        a = block_argmax(a, sh_am);
+        float s = 0.f;
+        for (int v = tid; v < p.eot; v += kSampleThreads) s += expf(__half2float(srow[v]) - a.v);
+        s = block_sum(s, sh_f);
+        if (tid == 0) {
+            if (p.align_prob) p.align_prob[(long long)b * p.tokens_stride + cur_len] = tok < p.eot ? expf(__half2float(srow[tok]) - a.v) / s : 0.f;
+            if (cur_len < p.tokens_stride) trow[cur_len] = tok;
+            out_len[b] = cur_len - n_initial + 1;
+        }
+        return;
+    }
 
     const bool first = (cur_len == n_initial);
     const int last_ts = st[0], pen_ts = st[1], have_ts = st[2], ts_last = st[3];

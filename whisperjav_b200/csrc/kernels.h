@@ -126,8 +126,15 @@ int launch_attn_dec_self(const __half* qkv, __half* kv_cache, __half* out, const
                          int n_ctx, cudaStream_t s, const short* anc = nullptr, long long anc_parity_stride = 0);
 // Decoder single-token cross-attention over kv [B][2H][T][64].
 // kv_div (beam search): row b reads the K/V of window b / kv_div
+// capture (word-timestamp alignment pass): scaled scores of the position *step are also written, fp16, to
+// base[b * b_stride + h * head_stride + *step * T + t]
+struct CrossCapture {
+    __half* base = nullptr;
+    long long b_stride = 0, head_stride = 0;
+    const int* step = nullptr;
+};
 int launch_attn_dec_cross(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T,
-                          cudaStream_t s, int kv_div = 1);
+                          cudaStream_t s, int kv_div = 1, const CrossCapture* capture = nullptr);
 
 // ---- decoder token logic (decode.cu) -------------------------------------------------------
 struct DecodeCtl {            // device-resident control block, one per decode run
@@ -150,6 +157,11 @@ struct DecodeParams {
     __half* trace_logits = nullptr;
     int* trace_sampled = nullptr;
     const int* trace_forced = nullptr;
+    // word-timestamp alignment pass (teacher-forced, timing.py::find_alignment): row b is fed align_len[b] tokens in all (it is
+    // finished after the step that feeds its last one, EOT included -- no EOT latch) and align_prob[b][p] receives
+    // softmax(raw logits[: eot])[forced token at p]
+    const int* align_len = nullptr;
+    float* align_prob = nullptr;
 };
 int launch_embed(const int* tokens, int tokens_stride, const __half* emb, const __half* pos, __half* x, const DecodeCtl* ctl, int B,
                  int n, cudaStream_t s, long long parity_stride = 0);
@@ -174,6 +186,11 @@ int launch_sample(const __half* logits, const unsigned char* suppress_mask, int*
                   float* no_speech_prob, int* out_len, unsigned char* done, DecodeCtl* ctl, const DecodeParams& p, cudaStream_t s);
 
 int launch_advance(DecodeCtl* ctl, cudaStream_t s);
+
+// ---- word-timestamp alignment (align.cu) ------------------------------------------------------
+size_t align_workspace_bytes(int B, int n_sel, int n_steps, int T);
+int launch_align(const __half* qk, int B, int n_sel, int n_steps, int T, const int* n_tok, const int* row_begin, const int* n_rows,
+                 const int* n_frames2, int medfilt, float* matrix, int* jump, void* workspace, size_t ws_bytes, cudaStream_t s);
 
 // ---- VAD (vad.cu) --------------------------------------------------------------------------
 struct VadArgs;

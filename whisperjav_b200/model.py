@@ -133,6 +133,24 @@ def detokenize(ids: Sequence[int]) -> str:
     return "".join(chr(0x4E00 + (int(t) % 20992)) for t in ids)
 
 
+def detokenize_with_specials(tok: "Tokens"):
+    """``tokenizer.decode_with_timestamps`` stand-in for the word splitter: text ids through the detokenizer, EOT as its tag."""
+    def decode(ids):
+        out, run = [], []
+        for t in ids:
+            if t >= tok.eot:
+                if run:
+                    out.append(detokenize(run))
+                    run = []
+                out.append("<|endoftext|>" if t == tok.eot else f"<|{t}|>")
+            else:
+                run.append(t)
+        if run:
+            out.append(detokenize(run))
+        return "".join(out)
+    return decode
+
+
 def compression_ratio(text: str) -> float:
     raw = text.encode("utf-8")
     return len(raw) / len(zlib.compress(raw))
@@ -352,6 +370,89 @@ class WhisperB200:
         res = self.decode_features(xa, _trace=trace, **kw)
         return res, trace
 
+    def align_windows(self, xa: torch.Tensor, text_tokens: Sequence[Sequence[int]], num_frames: Sequence[int], *, language="ja",
+                      task="transcribe", medfilt_width: int = 7, return_matrix: bool = False):
+        """timing.py::find_alignment for B windows in one device pass (wjb_decode_set_align + wjb_align_dtw): the decoder is
+        teacher-forced over [sot sequence, <|notimestamps|>, text tokens, <|endoftext|>], the cross-attention scores of the
+        alignment heads are captured, turned into the token x frame matrix and aligned by DTW.  Per window returns
+        (jump_frames int array [n_text + 1], token_probs float array [n_text]); windows without text tokens get empty arrays."""
+        d = self.dims
+        B = xa.shape[0]
+        tok = Tokens(d.n_vocab, language, task)
+        sot = [tok.sot, tok.language_token, tok.task_token]
+        n_initial = len(sot) + 1
+        seqs = [sot + [tok.no_timestamps] + [int(t) for t in tt] + [tok.eot] for tt in text_tokens]
+        live = [b for b in range(B) if len(text_tokens[b]) > 0]
+        empty = (np.zeros(0, np.int32), np.zeros(0, np.float32))
+        if not live:
+            return [empty] * B
+        if len(live) < B:
+            sub = self.align_windows(xa[torch.tensor(live, device=self.device)].contiguous(), [text_tokens[b] for b in live],
+                                     [num_frames[b] for b in live], language=language, task=task, medfilt_width=medfilt_width,
+                                     return_matrix=return_matrix)
+            out = [empty + ((None,) if return_matrix else ())] * B
+            for b, r in zip(live, sub):
+                out[b] = r
+            return out
+        max_len = max(len(q) for q in seqs)
+        if max_len > d.n_text_ctx:
+            raise ValueError("alignment sequence longer than n_text_ctx")
+        sample_len = max_len - n_initial + 1
+        stride = n_initial + sample_len + 1
+        opts = _lib.DecodeOpts()
+        opts.n_initial, opts.sot_index, opts.sample_len = n_initial, 0, sample_len
+        opts.eot, opts.no_speech, opts.no_timestamps, opts.timestamp_begin = tok.eot, tok.no_speech, tok.no_timestamps, tok.timestamp_begin
+        opts.suppress_blank, opts.blank_token, opts.apply_timestamp_rules, opts.max_initial_timestamp_index = 0, tok.blank, 0, -1
+        opts.tokens_stride, opts.check_every, opts.temperature, opts.seed = stride, 8, 0.0, 0
+        dev = self.device
+        with torch.cuda.device(dev):
+            kv = self._buf("cross_kv", self.lib.wjb_cross_kv_bytes(self._h, B))
+            _lib.check(self.lib.wjb_cross_kv(self._h, _lib.ptr(xa), B, _lib.ptr(kv), _lib.stream_ptr()), "wjb_cross_kv")
+            ws_bytes = self.lib.wjb_decode_workspace_bytes(self._h, B)
+            ws = self._buf("dec_ws", ws_bytes)
+            tokens = torch.zeros(B, stride, dtype=torch.int32)
+            forced = torch.full((B, stride), tok.eot, dtype=torch.int32)
+            for b, q in enumerate(seqs):
+                tokens[b, :n_initial] = torch.tensor(q[:n_initial], dtype=torch.int32)
+                forced[b, : len(q)] = torch.tensor(q, dtype=torch.int32)
+            tokens, forced = tokens.to(dev), forced.to(dev)
+            n_tok = torch.tensor([len(q) for q in seqs], dtype=torch.int32, device=dev)
+            row_begin = torch.full((B,), len(sot), dtype=torch.int32, device=dev)
+            n_rows = torch.tensor([len(q) - len(sot) - 1 for q in seqs], dtype=torch.int32, device=dev)
+            nf2 = torch.tensor([int(n) // 2 for n in num_frames], dtype=torch.int32, device=dev)
+            qk = self._buf("align_qk", self.lib.wjb_align_qk_bytes(self._h, B, max_len))
+            prob = torch.zeros(B, stride, dtype=torch.float32, device=dev)
+            slp = torch.zeros(3, B, dtype=torch.float32, device=dev)
+            olen = torch.zeros(B, dtype=torch.int32, device=dev)
+            steps = C.c_int(0)
+            _lib.check(self.lib.wjb_decode_set_trace(self._h, None, 0, None, _lib.ptr(forced)), "wjb_decode_set_trace")
+            _lib.check(self.lib.wjb_decode_set_align(self._h, _lib.ptr(qk), max_len, _lib.ptr(n_tok), _lib.ptr(prob)), "wjb_decode_set_align")
+            try:
+                _lib.check(self.lib.wjb_decode_greedy(self._h, _lib.ptr(kv), B, C.byref(opts), None, _lib.ptr(tokens), _lib.ptr(slp[0]),
+                                                     _lib.ptr(slp[1]), _lib.ptr(olen), _lib.ptr(ws), ws_bytes, C.byref(steps),
+                                                     _lib.stream_ptr()), "wjb_decode_greedy (alignment pass)")
+            finally:
+                self.lib.wjb_decode_set_align(self._h, None, 0, None, None)
+                self.lib.wjb_decode_set_trace(self._h, None, 0, None, None)
+            matrix = torch.zeros(B, max_len, d.n_audio_ctx, dtype=torch.float32, device=dev)
+            jump = torch.zeros(B, max_len, dtype=torch.int32, device=dev)
+            aws_bytes = self.lib.wjb_align_workspace_bytes(self._h, B, max_len)
+            aws = self._buf("align_ws", aws_bytes)
+            _lib.check(self.lib.wjb_align_dtw(self._h, _lib.ptr(qk), B, max_len, _lib.ptr(n_tok), _lib.ptr(row_begin), _lib.ptr(n_rows),
+                                             _lib.ptr(nf2), int(medfilt_width), _lib.ptr(matrix), _lib.ptr(jump), _lib.ptr(aws), aws_bytes,
+                                             _lib.stream_ptr()), "wjb_align_dtw")
+            h_jump, h_prob = jump.cpu().numpy(), prob.cpu().numpy()
+        self.stats["decode_steps"] += steps.value
+        self.stats["device_passes"] += 1
+        out = []
+        for b, q in enumerate(seqs):
+            n_text = len(q) - n_initial - 1
+            r = (h_jump[b, : n_text + 1].copy(), h_prob[b, n_initial: n_initial + n_text].copy())
+            if return_matrix:
+                r = r + (matrix[b, len(sot): len(q) - 1, : int(num_frames[b]) // 2].cpu(),)
+            out.append(r)
+        return out
+
     def _decode_beam(self, xa, opts, mask, initial, tok, beam: int, patience, length_penalty, language) -> List[DecodingResult]:
         """upstream decoding.py::DecodingTask.run with BeamSearchDecoder: the device runs update() for every step
         (``wjb_decode_beam``: rows = windows x beams, cache ancestry tables instead of cache permutation); finalize() and the
@@ -450,7 +551,7 @@ class WhisperB200:
         arrs = [a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a) for a in audios]
         arrs = [a.astype(np.float32, copy=False).reshape(-1) for a in arrs]
         content = [len(a) // HOP_LENGTH for a in arrs]
-        state = [{"seek": 0, "all_tokens": list(initial_prompt or []), "reset": 0, "segments": []} for _ in range(n)]
+        state = [{"seek": 0, "all_tokens": list(initial_prompt or []), "reset": 0, "segments": [], "last_speech": 0.0} for _ in range(n)]
         init_len = len(initial_prompt or [])
         for st in state:
             st["reset"] = 0
@@ -483,9 +584,12 @@ class WhisperB200:
                 results = self._decode_with_fallback(xa, prompts, temps, best_of, language, task, decode_options,
                                                      compression_ratio_threshold, logprob_threshold, no_speech_threshold)
                 _mark("decode")
+                pend = [self._slice(state[i], results[j], tok, sizes[j], no_speech_threshold, logprob_threshold) for j, i in enumerate(chunk)]
+                if word_timestamps:
+                    self._word_timestamps(xa, pend, sizes, tok, language, task, prepend_punctuations, append_punctuations,
+                                          [state[i] for i in chunk])
                 for j, i in enumerate(chunk):
-                    self._advance(state[i], results[j], tok, sizes[j], no_speech_threshold, logprob_threshold,
-                                  condition_on_previous_text)
+                    self._commit(state[i], pend[j], results[j], condition_on_previous_text)
                 _mark("advance")
         if _trace:
             import sys
@@ -590,10 +694,9 @@ class WhisperB200:
         return results
 
     @staticmethod
-    def _advance(st: dict, result: DecodingResult, tok: Tokens, segment_size: int, no_speech_threshold, logprob_threshold,
-                 condition_on_previous_text: bool) -> None:
-        """One iteration of upstream transcribe()'s seek loop for one clip (thresholds, timestamp-token
-        slicing, seek advance)."""
+    def _slice(st: dict, result: DecodingResult, tok: Tokens, segment_size: int, no_speech_threshold, logprob_threshold) -> dict:
+        """One iteration of upstream transcribe()'s seek loop for one clip, up to the word-timestamp hook: the no-speech skip,
+        timestamp-token slicing into segments and the provisional seek.  Returns {"skip", "current", "seek", "single_ending"}."""
         seek = st["seek"]
         tokens = result.tokens
         if no_speech_threshold is not None:
@@ -601,8 +704,7 @@ class WhisperB200:
             if logprob_threshold is not None and result.avg_logprob > logprob_threshold:
                 should_skip = False
             if should_skip:
-                st["seek"] = seek + segment_size
-                return
+                return {"skip": True, "current": [], "seek": seek + segment_size, "single_ending": False}
         time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
         precision = 0.02
         fields = {"temperature": result.temperature, "avg_logprob": result.avg_logprob,
@@ -626,19 +728,59 @@ class WhisperB200:
                                    time_offset + (piece[-1] - tok.timestamp_begin) * precision, piece))
                 last = cut
             if single_ending:
-                st["seek"] = seek + segment_size
+                new_seek = seek + segment_size
             else:
-                st["seek"] = seek + (tokens[last - 1] - tok.timestamp_begin) * 2
+                new_seek = seek + (tokens[last - 1] - tok.timestamp_begin) * 2
         else:
             duration = segment_size * HOP_LENGTH / SAMPLE_RATE
             stamps = [t for t in tokens if t >= tok.timestamp_begin]
             if stamps and stamps[-1] != tok.timestamp_begin:
                 duration = (stamps[-1] - tok.timestamp_begin) * precision
             current.append(seg(time_offset, time_offset + duration, tokens))
-            st["seek"] = seek + segment_size
+            new_seek = seek + segment_size
+        return {"skip": False, "current": current, "seek": new_seek, "single_ending": single_ending}
+
+    def _word_timestamps(self, xa, pend: List[dict], sizes: List[int], tok: Tokens, language, task, prepend_punctuations,
+                         append_punctuations, states: List[dict]) -> None:
+        """upstream transcribe()'s ``if word_timestamps:`` block for every window of a device pass: one batched alignment pass
+        (``align_windows``), then per window ``add_word_timestamps`` and the seek / last_speech_timestamp updates."""
+        from . import timing as TM
+        text = [[t for s in p["current"] for t in s["tokens"] if t < tok.eot] if not p["skip"] else [] for p in pend]
+        aligned = self.align_windows(xa, text, sizes, language=language, task=task)
+        for p, st, tt, (jump, probs) in zip(pend, states, text, aligned):
+            if p["skip"]:
+                continue
+            alignment = TM.words_from_alignment(tt, jump, probs, detokenize_with_specials(tok), tok.language, tok.eot)
+            st["last_speech"] = TM.add_word_timestamps(p["current"], alignment, tok.eot, prepend_punctuations, append_punctuations,
+                                                       st["last_speech"])
+            time_offset = float(st["seek"] * HOP_LENGTH / SAMPLE_RATE)
+            if not p["single_ending"]:
+                lwe = TM.last_word_end(p["current"])
+                if lwe is not None and lwe > time_offset:
+                    p["seek"] = round(lwe * 100)  # FRAMES_PER_SECOND
+            lwe = TM.last_word_end(p["current"])
+            if lwe is not None:
+                st["last_speech"] = lwe
+
+    @staticmethod
+    def _advance(st: dict, result: DecodingResult, tok: Tokens, segment_size: int, no_speech_threshold, logprob_threshold,
+                 condition_on_previous_text: bool) -> None:
+        """One whole seek-loop iteration without word timestamps (= _slice + _commit)."""
+        WhisperB200._commit(st, WhisperB200._slice(st, result, tok, segment_size, no_speech_threshold, logprob_threshold), result,
+                            condition_on_previous_text)
+
+    @staticmethod
+    def _commit(st: dict, p: dict, result: DecodingResult, condition_on_previous_text: bool) -> None:
+        """The tail of the seek-loop iteration: clear instantaneous / empty segments, append, advance the seek, reset the prompt."""
+        st["seek"] = p["seek"]
+        if p["skip"]:
+            return
+        current = p["current"]
         for s in current:
             if s["start"] == s["end"] or s["text"].strip() == "":
                 s["text"], s["tokens"] = "", []
+                if "words" in s:
+                    s["words"] = []
         base = len(st["segments"])
         st["segments"].extend({"id": base + k, **s} for k, s in enumerate(current))
         st["all_tokens"].extend(t for s in current for t in s["tokens"])
