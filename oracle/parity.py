@@ -35,8 +35,8 @@ def fp16_quantum(x: float) -> float:
     return 2.0 ** (math.floor(math.log2(x)) - 10)
 
 
-def decode_parity(model, weights, dims, xa: torch.Tensor, *, tie_quanta: float = 4.0, logit_quanta: float = 6.0,
-                  prepared=None, **decode_kw) -> Dict:
+def decode_parity(model, weights, dims, xa: torch.Tensor, *, tie_quanta: float = 4.0, logit_quanta: float = 16.0,
+                  logit_rms_quanta: float = 3.0, prepared=None, **decode_kw) -> Dict:
     """Greedy decode of encoder output ``xa`` (device tensor) on the GPU vs the oracle.  ``decode_kw`` are DecodingOptions
     fields understood by both sides (language, without_timestamps, max_initial_timestamp, sample_len, suppress_tokens ...).
     Returns a report dict; ``report["ok"]`` is the verdict, ``report["failures"]`` says why not."""
@@ -49,20 +49,24 @@ def decode_parity(model, weights, dims, xa: torch.Tensor, *, tie_quanta: float =
                         forced_tokens=[r.tokens for r in res])
     B = xa.shape[0]
     rows, failures = [], []
-    all_dq, all_margin = [], []
+    all_dq, all_margin, all_rms = [], [], []
     for b in range(B):
         toks = res[b].tokens
         n_steps = min(len(toks) + 1, len(rl))  # the step that produced EOT counts (unless sample_len ran out first)
         n_steps = min(n_steps, gl.shape[0] - (n_initial - 1))
-        dq, ties, bad = [], [], []
+        dq, drms, ties, bad = [], [], [], []
         for i in range(n_steps):
             g = gl[n_initial - 1 + i, b]
             r = rl[i][b]
             q = fp16_quantum(float(r.max()))
             d = float((g - r).abs().max()) / q
+            rms = float((g - r).pow(2).mean().sqrt()) / q
             dq.append(d)
-            if d > logit_quanta:
-                bad.append({"step": i, "dlogit_quanta": d})
+            drms.append(rms)
+            # two numbers per step: the largest difference over the 51 k vocabulary entries (a Gaussian extreme, ~4.5 x the
+            # rms) and the rms itself; rounding differences alone give rms ~ 1 quantum (scripts/synth_chaos.py)
+            if d > logit_quanta or rms > logit_rms_quanta:
+                bad.append({"step": i, "dlogit_quanta": d, "rms_quanta": rms})
         picks, gaps = ref[b].picks, ref[b].forced_gap
         fed = list(toks) + [opts_eot(dims)]
         for i in range(min(len(picks), n_steps)):
@@ -71,10 +75,12 @@ def decode_parity(model, weights, dims, xa: torch.Tensor, *, tie_quanta: float =
                 ties.append({"step": i, "gpu": int(fed[i]), "oracle": int(picks[i]), "gap_quanta": gaps[i] / q})
         row = {"b": b, "len": len(toks), "steps_checked": n_steps, "identical": not ties, "tie_breaks": ties,
                "dlogit_quanta_max": max(dq) if dq else 0.0, "dlogit_quanta_median": float(np.median(dq)) if dq else 0.0,
+               "dlogit_rms_quanta_max": max(drms) if drms else 0.0,
                "oracle_margin_min": min(ref[b].margins) if ref[b].margins else None,
                "sum_logprob_gpu": res[b].sum_logprob, "sum_logprob_oracle": ref[b].sum_logprob,
                "no_speech_gpu": res[b].no_speech_prob, "no_speech_oracle": ref[b].no_speech_prob}
         rows.append(row)
+        all_rms += drms
         all_dq += dq
         all_margin += list(ref[b].margins)
         if bad:
@@ -92,8 +98,9 @@ def decode_parity(model, weights, dims, xa: torch.Tensor, *, tie_quanta: float =
     return {"ok": not failures, "failures": failures, "windows": B, "identical_windows": sum(r["identical"] for r in rows),
             "steps_checked": n_steps_total, "tie_breaks": n_ties, "dlogit_quanta_max": max(all_dq) if all_dq else 0.0,
             "dlogit_quanta_p99": float(np.quantile(all_dq, 0.99)) if all_dq else 0.0,
+            "dlogit_rms_quanta_max": max(all_rms) if all_rms else 0.0,
             "oracle_margin_median": float(np.median(m)), "oracle_margin_frac_below_0.1": float((m < 0.1).mean()),
-            "tolerances": {"tie_quanta": tie_quanta, "logit_quanta": logit_quanta}, "rows": rows, "tokens": [r.tokens for r in res]}
+            "tolerances": {"tie_quanta": tie_quanta, "logit_quanta": logit_quanta, "logit_rms_quanta": logit_rms_quanta}, "rows": rows, "tokens": [r.tokens for r in res]}
 
 
 def opts_eot(dims) -> int:
@@ -137,3 +144,62 @@ def encoder_parity(model, weights, dims, mel_tm: torch.Tensor, tap_every: int = 
             out["taps"].append({"after_block": (k + 1) * tap_every, "rel_fro": float((t - r).norm() / r.norm())})
     out["ok"] = out["rel_fro"] <= 1e-2 and all(t["rel_fro"] <= 1e-2 for t in out.get("taps", []))
     return out, xa
+
+
+def transcribe_parity(model, weights, dims, clips: Sequence[np.ndarray], *, tie_quanta: float = 16.0, prepared=None, **kw) -> Dict:
+    """End to end (device mel + encoder + decoder + seek loop vs the oracle's) with nothing left unchecked after a divergence:
+    the oracle *follows the device window by window*.  For every window the device decoded (``_record_windows``) the oracle builds
+    that window from its own log-mel, runs its own encoder, is teacher-forced along the device's tokens and must find every one
+    of them to be its arg-max or within ``tie_quanta`` fp16 quanta of it (the two encoders differ by ~1e-3 relative, which moves
+    logits by a few quanta: larger than in the decoder-only comparison).  Then the host logic is replayed: the oracle's own
+    ``slice_segments`` on the device's tokens must give the device's segments and the next seek.  Clips whose every token is the
+    oracle's arg-max are, by induction, token-identical to the oracle's free-running transcribe()."""
+    pw = prepared if prepared is not None else wo.prepare_weights(weights, True)
+    dec_keys = {"language", "task", "without_timestamps", "max_initial_timestamp", "suppress_tokens", "suppress_blank", "sample_len"}
+    got = model.transcribe_batch(list(clips), _record_windows=True, **kw)
+    opts = wo.DecodingOptions(**{k: v for k, v in kw.items() if k in dec_keys})
+    tok = wo.SpecialTokens(dims.n_vocab, language=kw.get("language", "ja"), task=kw.get("task", "transcribe"))
+    failures, rows = [], []
+    for ci, (a, g) in enumerate(zip(clips, got)):
+        mel = wo.log_mel_spectrogram(a, dims.n_mels, padding=wo.N_SAMPLES)
+        content = mel.shape[-1] - wo.N_FRAMES
+        seek, ties, steps, segs = 0, 0, 0, []
+        for w in g["windows"]:
+            if w["seek"] != seek:
+                failures.append({"clip": ci, "why": "seek sequence", "device": w["seek"], "replayed": seek})
+                break
+            size = min(wo.N_FRAMES, content - seek)
+            win = wo.pad_or_trim(mel[:, seek: seek + size], wo.N_FRAMES)
+            ref = wo.decode(pw, dims, win[None], opts, True, forced_tokens=[w["tokens"]])[0]
+            fed = list(w["tokens"]) + [tok.eot]
+            for i, (pick, gap) in enumerate(zip(ref.picks, ref.forced_gap)):
+                steps += 1
+                if pick != fed[i]:
+                    ties += 1
+                    q = fp16_quantum(32.0)
+                    if not gap <= tie_quanta * q:
+                        failures.append({"clip": ci, "seek": seek, "step": i, "why": "device token is not a near-tie of the oracle's arg-max",
+                                         "gap_quanta": gap / q})
+            if abs(ref.avg_logprob - w["avg_logprob"]) > 0.03 or abs(ref.no_speech_prob - w["no_speech_prob"]) > 2e-3 + 0.05 * ref.no_speech_prob:
+                failures.append({"clip": ci, "seek": seek, "why": "avg_logprob / no_speech_prob", "device": [w["avg_logprob"], w["no_speech_prob"]],
+                                 "oracle": [ref.avg_logprob, ref.no_speech_prob]})
+            # host logic replay (transcribe.py's no-speech skip, slicing and seek advance) on the device's own decode result
+            nst, lpt = kw.get("no_speech_threshold", 0.6), kw.get("logprob_threshold", -1.0)
+            skip = nst is not None and w["no_speech_prob"] > nst and not (lpt is not None and w["avg_logprob"] > lpt)
+            if skip:
+                seek += size
+                continue
+            fields = {"temperature": w["temperature"], "avg_logprob": w["avg_logprob"], "no_speech_prob": w["no_speech_prob"]}
+            cur, adv = wo.slice_segments(w["tokens"], tok, seek, size, fields)
+            segs += cur
+            seek += adv
+        gs = g["segments"]
+        if len(gs) != len(segs) or any(x["tokens"] != y["tokens"] or x["seek"] != y["seek"] or abs(x["start"] - y["start"]) > 1e-9 or
+                                       abs(x["end"] - y["end"]) > 1e-9 for x, y in zip(gs, segs)):
+            failures.append({"clip": ci, "why": "segments differ from the oracle's slicing of the same tokens"})
+        if seek < content and not any(f["clip"] == ci for f in failures):
+            failures.append({"clip": ci, "why": "device stopped before the end of the clip", "seek": seek, "content": content})
+        rows.append({"clip": ci, "windows": len(g["windows"]), "steps": steps, "tie_breaks": ties, "identical": ties == 0, "segments": len(gs)})
+    return {"ok": not failures, "failures": failures, "clips": len(clips), "identical_clips": sum(r["identical"] for r in rows),
+            "steps_checked": sum(r["steps"] for r in rows), "tie_breaks": sum(r["tie_breaks"] for r in rows), "rows": rows,
+            "tolerances": {"tie_quanta": tie_quanta}}

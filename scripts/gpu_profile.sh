@@ -1,12 +1,14 @@
 #!/bin/bash
-# ncu evidence for one shortened step (large-v3, B=64): launch list + full captures of the top kernels.
+# ncu evidence for one shortened step (large-v3, B=64): launch list + full captures of the top kernels of every stage.
+# Kernel nodes of the decode CUDA graph are profiled individually (ncu's default graph-profiling mode).
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-export WJB_NO_GRAPH=1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
-    python scripts/profile_step.py --batch 64 --tokens 4 > gpurun_out/prof_launch.log 2>&1
+    python scripts/profile_step.py --batch 64 --tokens 4 --vad --align > gpurun_out/prof_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc|attn_encoder|logmel_kernel|layernorm" -c 14 \
     -o gpurun_out/prof_encoder -f python scripts/profile_step.py --batch 64 --tokens 2 > gpurun_out/prof_enc.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"attn_dec|gemm_step|sample_kernel" -s 44 -c 14 \
     -o gpurun_out/prof_decode -f python scripts/profile_step.py --batch 64 --tokens 3 > gpurun_out/prof_dec.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"vad_|align_" -c 8 \
+    -o gpurun_out/prof_vad_align -f python scripts/profile_step.py --batch 64 --tokens 12 --vad --align > gpurun_out/prof_va.log 2>&1
 ls -la gpurun_out/*.ncu-rep gpurun_out/launches.csv

@@ -18,14 +18,10 @@ ap.add_argument("--model", default="large-v3")
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--tokens", type=int, default=6)
 ap.add_argument("--reps", type=int, default=1)
-ap.add_argument("--fast-weights", action="store_true", help="random weights generated on the GPU (values irrelevant for timing)")
+ap.add_argument("--vad", action="store_true", help="also one VAD pass over the same clips (vad_features_kernel / vad_lstm_kernel)")
+ap.add_argument("--align", action="store_true", help="also one word-timestamp alignment pass (capture + align_* kernels)")
 args = ap.parse_args()
 dims = DIMS[args.model]
-sd = None
-if args.fast_weights:
-    from whisperjav_b200.synth import synth_weights
-    small = synth_weights(DIMS["tiny"], seed=1)
-    ref = synth_weights.__wrapped__ if hasattr(synth_weights, "__wrapped__") else None
 m = M.load_model(args.model, max_batch=args.batch)
 base = [speech_shaped_audio(30.0, 2000 + i) for i in range(4)]
 audio = torch.stack([torch.from_numpy(base[i % 4]) for i in range(args.batch)]).cuda()
@@ -34,5 +30,11 @@ for _ in range(args.reps):
     mel = m.log_mel(audio, ns, n_frames=3000, layout="time")
     xa = m.encode(mel)
     res = m.decode_features(xa, language="ja", without_timestamps=True, sample_len=args.tokens)
+if args.vad:
+    from whisperjav_b200.vad import VadB200
+    VadB200().probs(audio, ns)
+if args.align:
+    eot = M.Tokens(dims.n_vocab, "ja").eot
+    m.align_windows(xa, [[t for t in r.tokens if t < eot] or [11] for r in res], [3000] * args.batch, language="ja")
 torch.cuda.synchronize()
 print("ok", [len(r.tokens) for r in res][:4])

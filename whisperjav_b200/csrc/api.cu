@@ -584,22 +584,29 @@ static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B
             if (int e = launch_layernorm(A, ln_g, ln_b, w.h, B, K, s)) return e;
             A = w.h;
         }
-        if (gemm_step_supported(B, N, K)) {  // the cluster split-K kernel written for exactly this shape class (gemm_step.cu)
-            StepGemmArgs g;
-            g.A = A;
-            g.a_row_stride = K;
-            g.rows = B;
-            g.K = K;
-            g.W = W;
-            g.N = N;
-            g.ldw = ldw;
-            g.bias = bias;
-            g.residual = res;
-            g.out = out;
-            g.out_row_stride = out_stride;
-            g.flags = flags;
-            g.w_constant = true;
-            return launch_gemm_step(g, s);
+        // the cluster split-K kernel written for exactly this shape class (gemm_step.cu) takes <= 128 rows: larger row counts
+        // (64 windows x beam 3 = 192) go through it in row chunks -- the weights stream twice, still well ahead of the general kernel
+        const int chunk = B <= 128 ? B : (B + 1) / 2 <= 128 ? (B + 1) / 2 : 128;
+        if (gemm_step_supported(chunk, N, K) && gemm_step_supported(B - (B - 1) / chunk * chunk, N, K)) {
+            for (int r0 = 0; r0 < B; r0 += chunk) {
+                const int rows = B - r0 < chunk ? B - r0 : chunk;
+                StepGemmArgs g;
+                g.A = A + (long long)r0 * K;
+                g.a_row_stride = K;
+                g.rows = rows;
+                g.K = K;
+                g.W = W;
+                g.N = N;
+                g.ldw = ldw;
+                g.bias = bias;
+                g.residual = res ? res + (long long)r0 * out_stride : nullptr;
+                g.out = out + (long long)r0 * out_stride;
+                g.out_row_stride = out_stride;
+                g.flags = flags;
+                g.w_constant = true;
+                if (int e = launch_gemm_step(g, s)) return e;
+            }
+            return 0;
         }
         GemmArgs q;
         q.A = A;

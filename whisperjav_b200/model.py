@@ -520,7 +520,7 @@ class WhisperB200:
                          carry_initial_prompt: bool = False, prepend_punctuations: str = "\"'“¿([{-",
                          append_punctuations: str = "\"'.。,，!！?？:：”)]}、", clip_timestamps: Union[str, List[float]] = "0",
                          hallucination_silence_threshold: Optional[float] = None, pinned_audio: Optional[torch.Tensor] = None,
-                         **decode_options) -> List[dict]:
+                         _record_windows: bool = False, **decode_options) -> List[dict]:
         """Independent clips (each: fp32 mono 16 kHz) -> one upstream-shaped result dict per clip.  Every keyword of upstream
         ``whisper.transcribe()`` is accepted by name; names upstream would reject raise TypeError as ``DecodingOptions(**kw)`` does."""
         unknown = set(decode_options) - _DECODE_KEYS
@@ -551,7 +551,8 @@ class WhisperB200:
         arrs = [a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a) for a in audios]
         arrs = [a.astype(np.float32, copy=False).reshape(-1) for a in arrs]
         content = [len(a) // HOP_LENGTH for a in arrs]
-        state = [{"seek": 0, "all_tokens": list(initial_prompt or []), "reset": 0, "segments": [], "last_speech": 0.0} for _ in range(n)]
+        state = [{"seek": 0, "all_tokens": list(initial_prompt or []), "reset": 0, "segments": [], "last_speech": 0.0, "windows": []}
+                 for _ in range(n)]
         init_len = len(initial_prompt or [])
         for st in state:
             st["reset"] = 0
@@ -584,6 +585,11 @@ class WhisperB200:
                 results = self._decode_with_fallback(xa, prompts, temps, best_of, language, task, decode_options,
                                                      compression_ratio_threshold, logprob_threshold, no_speech_threshold)
                 _mark("decode")
+                if _record_windows:  # parity tests: what every decoded window returned, before the host logic touches it
+                    for j, i in enumerate(chunk):
+                        r = results[j]
+                        state[i]["windows"].append({"seek": state[i]["seek"], "size": sizes[j], "tokens": list(r.tokens), "avg_logprob": r.avg_logprob,
+                                                    "no_speech_prob": r.no_speech_prob, "temperature": r.temperature})
                 pend = [self._slice(state[i], results[j], tok, sizes[j], no_speech_threshold, logprob_threshold) for j, i in enumerate(chunk)]
                 if word_timestamps:
                     self._word_timestamps(xa, pend, sizes, tok, language, task, prepend_punctuations, append_punctuations,
@@ -600,6 +606,8 @@ class WhisperB200:
         for i in range(n):
             toks = state[i]["all_tokens"][init_len:]
             outs.append({"text": detokenize([t for t in toks if t < tok.eot]), "segments": state[i]["segments"], "language": language})
+            if _record_windows:
+                outs[-1]["windows"] = state[i]["windows"]
         return outs
 
     # -- helpers -------------------------------------------------------------------------------
