@@ -223,6 +223,11 @@ size_t wjb_vad_workspace_bytes(int n_clips, int n_windows);
 int wjb_vad_forward(const float* audio, int64_t audio_stride, const int32_t* n_samples, int n_clips, const void* weights,
                     float* probs, int n_windows, void* workspace, void* stream);
 
+/* Frame head of the WhisperSeg-class gate (speech_segmentation/backends/whisperseg.py:355-393: 30 s window -> 80-mel ->
+ * Whisper-base-shaped encoder -> one logit per 20 ms frame -> sigmoid): prob[r] = sigmoid(x[r] . w + bias) for `rows` encoder
+ * frames x fp16 [rows][n]; the encoder itself is wjb_encoder_forward on a base-sized model handle. */
+int wjb_frame_head_f16(const void* x, const void* w, float bias, float* prob, int rows, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,8 +83,68 @@ def test_registration_with_reference_factories():
         from whisperjav.modules.subtitle_pipeline.protocols import TextGenerator
         seg = SpeechSegmenterFactory.create("b200-vad", config={"threshold": 0.4, "chunk_threshold_s": 2.5})
         assert isinstance(seg, SpeechSegmenter) and seg.chunk_threshold_s == 2.5
+        ws = SpeechSegmenterFactory.create("b200-whisperseg", config={"threshold": 0.35, "max_group_duration_s": 6.0})
+        assert isinstance(ws, SpeechSegmenter) and ws.name == "b200-whisperseg" and ws.max_speech_duration_s == 6.0
         gen = TextGeneratorFactory.create("b200-whisper", model_id="tiny", device="cuda", dtype="float16",
                                           no_repeat_ngram_size=0, max_new_tokens=444)
         assert isinstance(gen, TextGenerator)
+    finally:
+        sys.path.remove("/root/reference")
+
+
+def test_whisperseg_surface_and_postprocess_match_reference_defaults():
+    """Constructor keywords / defaults of whisperseg.py:80-141 and the probs -> segments -> groups chain on scripted frame
+    probabilities (the state machine itself is pinned by the reference-generated KATs in test_host_kats.py)."""
+    from whisperjav_b200.whisperseg import B200WhisperSegSegmenter
+    s = B200WhisperSegSegmenter(version="x")
+    assert (s.threshold, s.min_speech_duration_ms, s.min_silence_duration_ms, s.speech_pad_ms) == (0.35, 100, 100, 300)
+    assert (s.chunk_threshold_s, s.max_group_duration_s, s.max_speech_duration_s) == (1.0, 29.0, 29.0)
+    assert s.name == "b200-whisperseg" and s.get_supported_sample_rates() == [16000]
+    p = np.zeros(1500, np.float32)
+    p[100:200] = 0.9
+    p[260:300] = 0.9
+    r = s._postprocess(p, 30.0, 0.0)
+    # whisperseg.py (SURVEY 8c): p[100:200] = 0.9 -> one segment 1.700-4.300 s (2.0 - 0.3, 4.0 + 0.3); the second region is
+    # 1.2 s later, so its padding is clipped half way to the first and they fall into one group (gap < 1.0 s)
+    assert abs(r.segments[0].start_sec - 1.7) < 1e-9 and r.num_segments == 2 and r.num_groups == 1
+    assert B200WhisperSegSegmenter(chunk_threshold_s=None, chunk_threshold=2.0).chunk_threshold_s == 2.0
+
+
+@pytest.mark.skipif(not Path("/root/reference/whisperjav").exists(), reason="reference tree not present (GPU box)")
+def test_reference_vad_grouped_framer_drives_the_b200_segmenters(monkeypatch):
+    """The reference's own VadGroupedFramer (subtitle_pipeline/framers/vad_grouped.py:77-164) run with both B200 segmenters:
+    factory -> segment() -> groups -> TemporalFrames.  The device stage is replaced by scripted probabilities (no GPU here); the
+    frames must be exactly the groups of the reference's own state machines on those probabilities."""
+    sys.path.insert(0, "/root/reference")
+    try:
+        whisperjav_b200.register()
+        from whisperjav.modules.subtitle_pipeline.framers.vad_grouped import VadGroupedFramer
+        from whisperjav_b200.segmenter import B200SpeechSegmenter
+        from whisperjav_b200.whisperseg import B200WhisperSegSegmenter
+        audio = np.zeros(480000, np.float32)
+
+        class FakeVad:
+            device = "cpu"
+
+            def probs(self, a, ns):
+                import torch
+                p = torch.zeros(a.shape[0], (a.shape[1] + 511) // 512)
+                p[:, 100:200] = 0.9
+                p[:, 400:500] = 0.9
+                return p
+        monkeypatch.setattr(B200SpeechSegmenter, "_ensure_model", lambda self: FakeVad())
+        fr = VadGroupedFramer(segmenter_backend="b200-vad", max_group_duration_s=6.0, chunk_threshold_s=2.5).frame(audio, 16000)
+        assert fr.metadata["segmenter_backend"] == "b200-vad" and fr.metadata["total_segments"] == 2
+        assert [(round(f.start, 3), round(f.end, 3)) for f in fr.frames] == [(2.5, 7.7), (12.1, 17.3)]
+
+        def fake_probs(self, clips):
+            p = np.zeros(1500, np.float32)
+            p[100:200] = 0.9
+            return [p for _ in clips]
+        monkeypatch.setattr(B200WhisperSegSegmenter, "frame_probs", fake_probs)
+        fr = VadGroupedFramer(segmenter_backend="b200-whisperseg").frame(audio, 16000)
+        assert fr.metadata["segmenter_backend"] == "b200-whisperseg"
+        assert [(round(f.start, 3), round(f.end, 3)) for f in fr.frames] == [(1.7, 4.3)]     # SURVEY 8c: 2.0 - 0.3 .. 4.0 + 0.3
+        assert fr.metadata["speech_regions"] == [[(1.7, 4.3)]]
     finally:
         sys.path.remove("/root/reference")

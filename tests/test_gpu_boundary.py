@@ -116,3 +116,35 @@ def test_generator_batch_matches_single(tmp_path):
     assert len({tuple(r.metadata["tokens"]) for r in batch}) == 3
     g.unload()
     assert g.is_loaded is False
+
+
+def test_whisperseg_class_segmenter(diag_dir):
+    """The WhisperSeg-class gate end to end on the device: 30 s chunks -> HF-semantics 80-mel -> Whisper-base-shaped encoder ->
+    frame head -> probs, checked against the CPU oracle's encoder (sim fp16) + the same head; then the reference's state machine."""
+    from oracle import whisper_oracle as wo
+    from whisperjav_b200.whisperseg import B200WhisperSegSegmenter
+    seg = B200WhisperSegSegmenter(threshold=0.35, max_group_duration_s=6.0, chunk_threshold_s=1.0)
+    clips = [speech_shaped_audio(41.0, 31), speech_shaped_audio(7.0, 32)]
+    probs = seg.frame_probs(clips)
+    assert [len(p) for p in probs] == [3000, 1500] and all(np.all((p >= 0) & (p <= 1)) for p in probs)
+    # oracle: HF-semantics mel (raw audio padded to 30 s) -> encoder -> head
+    m = seg._model
+    dims = m.dims
+    from whisperjav_b200.synth import synth_weights
+    w = wo.prepare_weights(synth_weights(dims, seed=seg._seed), True)
+    hw, hb = seg._head
+    a = np.zeros(480000, np.float32)
+    a[: len(clips[1])] = clips[1]
+    mel = wo.log_mel_spectrogram(a, 80)[None]
+    xa = wo.encoder_forward(w, dims, mel.half().float(), True)
+    ref = torch.sigmoid(xa[0] @ hw.float().cpu() + hb).numpy()
+    err = float(np.abs(probs[1] - ref).max())
+    (diag_dir / "whisperseg.json").write_text(json.dumps({"err": err}))
+    assert err <= 2e-2, err
+    res = seg.segment_batch(clips)
+    assert res[0].method == "b200-whisperseg" and abs(res[0].audio_duration_sec - 41.0) < 1e-6
+    for r in res:
+        for g in r.groups:
+            assert g[-1].end_sec - g[0].start_sec <= 6.0 + 1e-6 or len(g) == 1
+    assert seg.segment(np.zeros(0, np.float32)).segments == []
+    seg.cleanup()

@@ -16,6 +16,8 @@ def register() -> dict:
         from whisperjav.modules.speech_segmentation import factory as sf  # type: ignore
         sf._BACKEND_REGISTRY["b200-vad"] = "whisperjav_b200.segmenter.B200SpeechSegmenter"
         sf._BACKEND_DEPENDENCIES["b200-vad"] = {"packages": [], "install_hint": "", "always_available": True}
+        sf._BACKEND_REGISTRY["b200-whisperseg"] = "whisperjav_b200.whisperseg.B200WhisperSegSegmenter"
+        sf._BACKEND_DEPENDENCIES["b200-whisperseg"] = {"packages": [], "install_hint": "", "always_available": True}
         done["speech_segmenter"] = True
     except Exception:
         pass

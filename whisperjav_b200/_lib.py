@@ -81,6 +81,7 @@ _SIGS = {
     "wjb_attention_cross_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "wjb_profile_enable": (None, [C.c_int]),
     "wjb_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
+    "wjb_frame_head_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "wjb_vad_weights_bytes": (C.c_size_t, []),
     "wjb_vad_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "wjb_vad_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

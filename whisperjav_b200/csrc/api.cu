@@ -1000,6 +1000,11 @@ int wjb_gemm_f16_splitk(const void* A, int64_t a_row_stride, int rows, int K, co
     return launch_gemm(g, (cudaStream_t)stream);
 }
 
+int wjb_frame_head_f16(const void* x, const void* w, float bias, float* prob, int rows, int n, void* stream) {
+    if (!x || !w || !prob) return set_error("frame_head: null argument");
+    return launch_frame_head((const __half*)x, (const __half*)w, bias, prob, rows, n, (cudaStream_t)stream);
+}
+
 int wjb_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int n, void* stream) {
     if (int e = ensure_init()) return e;
     return launch_layernorm((const __half*)x, (const __half*)gamma, (const __half*)beta, (__half*)out, rows, n, (cudaStream_t)stream);

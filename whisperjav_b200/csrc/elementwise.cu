@@ -86,6 +86,38 @@ int launch_layernorm(const __half* x, const __half* gamma, const __half* beta, _
     return 0;
 }
 
+// Frame classifier head of the WhisperSeg-class VAD (speech_segmentation/backends/whisperseg.py:355-393: encoder states ->
+// one logit per 20 ms frame -> sigmoid): prob[r] = sigmoid(x[r] . w + b), one warp per frame row, fp32 accumulate.
+__global__ void __launch_bounds__(256) frame_head_kernel(const __half* __restrict__ x, const __half* __restrict__ w, float bias,
+                                                         float* __restrict__ prob, int rows, int n) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)warp * n);
+    const uint4* wr = reinterpret_cast<const uint4*>(w);
+    float acc = 0.f;
+    for (int i = lane; i < (n >> 3); i += 32) {
+        const uint4 a = xr[i], b = __ldg(wr + i);
+        const __half2* ah = reinterpret_cast<const __half2*>(&a);
+        const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 af = __half22float2(ah[j]), bf = __half22float2(bh[j]);
+            acc = fmaf(af.x, bf.x, acc);
+            acc = fmaf(af.y, bf.y, acc);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) prob[warp] = 1.0f / (1.0f + expf(-(acc + bias)));
+}
+
+int launch_frame_head(const __half* x, const __half* w, float bias, float* prob, int rows, int n, cudaStream_t s) {
+    if (n % 8) return set_error("frame_head: n must be a multiple of 8");
+    if (rows <= 0) return 0;
+    frame_head_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, w, bias, prob, rows, n);
+    WJB_CHECK_LAUNCH("frame_head");
+    return 0;
+}
+
 // out[b][t][k*C + c] = xpad[b][stride*t + k][c]  (k = 0..2), 16-byte vectors along c.
 __global__ void im2col_k3_kernel(const uint4* __restrict__ xpad, uint4* __restrict__ out, int B, int T_out, int Cv, int stride,
                                  int T_in_padded) {

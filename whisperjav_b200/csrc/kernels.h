@@ -94,6 +94,7 @@ int gemm_step_init();
 void gemm_step_set_trace(void* buf);
 // ---- elementwise / normalisation (elementwise.cu) ------------------------------------------
 int launch_layernorm(const __half* x, const __half* gamma, const __half* beta, __half* out, int rows, int n, cudaStream_t s);
+int launch_frame_head(const __half* x, const __half* w, float bias, float* prob, int rows, int n, cudaStream_t s);
 int launch_im2col_k3(const __half* xpad, __half* out, int B, int T_out, int C, int stride, int T_in_padded, cudaStream_t s);
 
 // ---- log-mel (logmel.cu) -------------------------------------------------------------------
