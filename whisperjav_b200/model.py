@@ -219,15 +219,22 @@ class WhisperB200:
 
     # ------------------------------------------------------------------ stages
     def log_mel(self, audio: torch.Tensor, n_samples: torch.Tensor, n_frames: int = N_FRAMES, layout: str = "time",
-                reflect_total: int = 0) -> torch.Tensor:
+                reflect_total: int = 0, reuse: Optional[str] = None) -> torch.Tensor:
         """audio fp32 [B, S] on device, n_samples int32 [B] on device.
         layout "time": fp16 [B, n_frames + 2, n_mels] (rows 0 / n_frames+1 are the conv zero pad);
-        layout "mel":  fp16 [B, n_mels, n_frames] (upstream layout)."""
+        layout "mel":  fp16 [B, n_mels, n_frames] (upstream layout).
+        ``reuse``: name of a cached output buffer (the transcribe loop's; the result is then only valid until the next call
+        with the same name) instead of a fresh allocation."""
         B = audio.shape[0]
         m = self.dims.n_mels
         ws = self._buf("mel_ws", self.lib.wjb_logmel_workspace_bytes(B, m))
         if layout == "time":
-            out = torch.zeros(B, n_frames + 2, m, dtype=torch.float16, device=self.device)
+            if reuse:
+                out = self._buf(reuse, B * (n_frames + 2) * m * 2)[: B * (n_frames + 2) * m * 2].view(torch.float16).view(B, n_frames + 2, m)
+                out[:, 0].zero_()       # the kernel writes every frame row (zeros past the content); only the two conv pad
+                out[:, -1].zero_()      # rows need clearing
+            else:
+                out = torch.zeros(B, n_frames + 2, m, dtype=torch.float16, device=self.device)
             tm, stride, row0 = 1, (n_frames + 2) * m, 1
         else:
             out = torch.empty(B, m, n_frames, dtype=torch.float16, device=self.device)
@@ -238,9 +245,10 @@ class WhisperB200:
                                               _lib.stream_ptr()), "wjb_logmel_f16")
         return out
 
-    def encode(self, mel_tm: torch.Tensor, tap_every: int = 0):
+    def encode(self, mel_tm: torch.Tensor, tap_every: int = 0, reuse: Optional[str] = None):
         """mel_tm fp16 [B, 3002, n_mels] -> audio features fp16 [B, 1500, n_state].  ``tap_every`` (parity tests): also return
-        the residual stream after every ``tap_every``-th block, fp16 [n_audio_layer // tap_every, B, 1500, n_state]."""
+        the residual stream after every ``tap_every``-th block, fp16 [n_audio_layer // tap_every, B, 1500, n_state].
+        ``reuse``: name of a cached output buffer (valid until the next call with that name)."""
         B = mel_tm.shape[0]
         d = self.dims
         if tap_every:
@@ -251,7 +259,11 @@ class WhisperB200:
             finally:
                 self.lib.wjb_encoder_set_tap(self._h, None, 0)
         assert mel_tm.shape[1] == 2 * d.n_audio_ctx + 2 and mel_tm.shape[2] == d.n_mels and mel_tm.is_contiguous()
-        out = torch.empty(B, d.n_audio_ctx, d.n_audio_state, dtype=torch.float16, device=self.device)
+        if reuse:
+            nbytes = B * d.n_audio_ctx * d.n_audio_state * 2
+            out = self._buf(reuse, nbytes)[:nbytes].view(torch.float16).view(B, d.n_audio_ctx, d.n_audio_state)
+        else:
+            out = torch.empty(B, d.n_audio_ctx, d.n_audio_state, dtype=torch.float16, device=self.device)
         nb = self.lib.wjb_encoder_workspace_bytes(self._h, B)
         ws = self._buf("enc_ws", nb)
         with torch.cuda.device(self.device):
@@ -579,7 +591,7 @@ class WhisperB200:
                 sizes = [min(N_FRAMES, content[i] - state[i]["seek"]) for i in chunk]
                 win = self._gather_windows(mels, chunk, [state[i]["seek"] for i in chunk], sizes)
                 _mark("gather")
-                xa = self.encode(win)
+                xa = self.encode(win, reuse="xa_loop")
                 _mark("encode")
                 prompts = [state[i]["all_tokens"][state[i]["reset"]:] for i in chunk]
                 results = self._decode_with_fallback(xa, prompts, temps, best_of, language, task, decode_options,
@@ -635,12 +647,14 @@ class WhisperB200:
         dev_ns = ns.to(self.device)
         # frames per clip rounded so short clips still give one full window directly
         nf = max(max_f, N_FRAMES)
-        return self.log_mel(dev_audio, dev_ns, n_frames=nf, layout="time"), nf
+        return self.log_mel(dev_audio, dev_ns, n_frames=nf, layout="time", reuse="mel_loop"), nf
 
     def _gather_windows(self, mels, chunk: List[int], seeks: List[int], sizes: List[int]) -> torch.Tensor:
         mel, nf = mels
         m = self.dims.n_mels
         if nf == N_FRAMES and all(s == 0 for s in seeks):
+            if chunk == list(range(mel.shape[0])):
+                return mel  # the whole clip batch in order: no copy
             idx = torch.tensor(chunk, device=self.device)
             return mel.index_select(0, idx).contiguous()
         win = torch.zeros(len(chunk), N_FRAMES + 2, m, dtype=torch.float16, device=self.device)
