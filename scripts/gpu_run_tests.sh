@@ -11,6 +11,7 @@ for f in ${@:-tests/test_gpu_*.py}; do
   rc=$?
   echo "$name rc=$rc" | tee -a gpurun_out/summary.txt
   tail -5 gpurun_out/$name.log
+  [ $rc -ne 0 ] && grep -E "^E  " gpurun_out/$name.log | cut -c1-400 | head -20
   [ $rc -ne 0 ] && status=1
 done
 exit $status

@@ -37,8 +37,8 @@ for n, v in seq:
     agg[n][1] += v
 tot = sum(v[1] for v in agg.values())
 md = [f"# {tag}: ncu launch list of one shortened hot-path step (large-v3, batch 64, 4 sampled tokens)\n",
-      "`ncu --metrics gpu__time_duration.sum --clock-control none` over `scripts/profile_step.py --batch 64 --tokens 4`, graphs disabled so",
-      "every decode kernel is listed.  Times are cold-cache and serialised: compare shares, not absolutes.\n",
+      "`ncu --metrics gpu__time_duration.sum --clock-control none` over `scripts/profile_step.py --batch 64 --tokens 4`, the kernel nodes of the decode graph are",
+      "listed individually.  Times are cold-cache and serialised: compare shares, not absolutes.\n",
       f"total {tot / 1000:.2f} ms over {len(seq)} launches\n", "| kernel | launches | total us | avg us | share |", "|---|---|---|---|---|"]
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     md.append(f"| `{k[:80]}` | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.2f} | {100 * v[1] / tot:.1f}% |")
@@ -60,8 +60,13 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_th
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "sm__cycles_elapsed.avg"]
-for rep in sorted(G.glob("prof_*.ncu-rep")):
-    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+reps = sorted(G.glob("prof_*.raw.csv")) + sorted(G.glob("prof_*.ncu-rep"))
+for rep in reps:
+    if rep.suffix == ".csv":
+        raw = rep.read_text()
+    else:
+        raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    raw = "\n".join(l for l in raw.splitlines() if not l.startswith("=="))
     rows = list(csv.reader(io.StringIO(raw)))
     if len(rows) < 3:
         continue
@@ -74,5 +79,5 @@ for rep in sorted(G.glob("prof_*.ncu-rep")):
             if k in ix:
                 d[k] = f"{r[ix[k]]} {units[ix[k]]}".strip()
         res.append(d)
-    (out / f"{tag}_{rep.stem}.json").write_text(json.dumps(res, indent=1))
+    (out / f"{tag}_{rep.name.split('.')[0]}.json").write_text(json.dumps(res, indent=1))
 print("wrote", sorted(p.name for p in out.glob(f"{tag}_*")))
