@@ -138,6 +138,13 @@ int wjb_decode_set_trace(wjb_model* m, void* logits_out, size_t logits_out_bytes
  * are host logic (whisperjav_b200/timing.py). */
 size_t wjb_align_qk_bytes(const wjb_model* m, int batch, int n_steps);
 int wjb_decode_set_align(wjb_model* m, void* qk_out, int n_steps, const int32_t* n_tokens, float* token_prob_out);
+/* Step 1 as ONE pass over whole sequences (every position of every window a GEMM row: one sweep of the decoder weights instead
+ * of one decode step per position): tokens int32 [B][tokens_stride] holds the n_tokens[b] tokens of every row (device memory),
+ * n_steps (a multiple of 8, <= 256) >= max n_tokens is the padded row count per window; same qk_out / token_prob_out layout as
+ * above (probabilities are softmax(logits[: eot])); cross_kv from wjb_cross_kv.  Workspace: wjb_align_prefill_workspace_bytes(m, batch, n_steps). */
+size_t wjb_align_prefill_workspace_bytes(const wjb_model* m, int batch, int n_steps);
+int wjb_align_prefill(wjb_model* m, const void* cross_kv, const int32_t* tokens, int tokens_stride, const int32_t* n_tokens, int batch,
+                      int n_steps, int eot, void* qk_out, float* token_prob_out, void* workspace, size_t workspace_bytes, void* stream);
 size_t wjb_align_workspace_bytes(const wjb_model* m, int batch, int n_steps);
 int wjb_align_dtw(wjb_model* m, const void* qk, int batch, int n_steps, const int32_t* n_tokens, const int32_t* row_begin,
                   const int32_t* n_rows, const int32_t* n_frames2, int medfilt_width, float* matrix, int32_t* jump_frames,

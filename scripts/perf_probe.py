@@ -1,5 +1,7 @@
-"""Kernel-level timing probe (CUDA events, after warm-up) through the C-ABI.  Scratch tool: writes
-gpurun_out/perf_probe.json.  Numbers here are per-kernel, inputs larger than L2."""
+"""Kernel-level timing probe (CUDA events, after warm-up) through the C-ABI, every kernel next to the library that does the same
+job in the reference's stack on the same box: cuBLAS (torch.matmul) for the GEMMs, cuDNN/flash SDPA for the encoder attention,
+torch layer_norm, torch.stft + matmul for the log-mel.  Writes gpurun_out/perf_probe.json (committed as profiles/<tag>_library_probe.json).
+Inputs are larger than L2."""
 import json
 import sys
 from pathlib import Path
@@ -68,7 +70,8 @@ res["attn_encoder"]["torch_sdpa_ms"] = ms2
 x = torch.randn(M, 1280, device=DEV, dtype=torch.float16)
 g = torch.ones(1280, device=DEV, dtype=torch.float16)
 ms = timeit(lambda: _lib.check(lib.wjb_layernorm_f16(_lib.ptr(x), _lib.ptr(g), _lib.ptr(g), _lib.ptr(out), M, 1280, _lib.stream_ptr()), "ln"))
-res["layernorm"] = {"ms": ms, "GBps": 2 * M * 1280 * 2 / ms / 1e6}
+res["layernorm"] = {"ms": ms, "GBps": 2 * M * 1280 * 2 / ms / 1e6,
+                    "torch_layer_norm_ms": timeit(lambda: torch.nn.functional.layer_norm(x, (1280,), g, g))}
 
 # cross attention decode
 qd = torch.randn(B, 1280, device=DEV, dtype=torch.float16)
@@ -86,7 +89,25 @@ ws = torch.zeros(lib.wjb_logmel_workspace_bytes(B, 128), dtype=torch.uint8, devi
 mel = torch.zeros(B, 3002, 128, dtype=torch.float16, device=DEV)
 ms = timeit(lambda: _lib.check(lib.wjb_logmel_f16(_lib.ptr(audio), 480000, _lib.ptr(ns), B, 128, _lib.ptr(filt), _lib.ptr(mel), 1, 3002 * 128, 1, 3000, 0,
                                                   _lib.ptr(ws), _lib.stream_ptr()), "mel"))
-res["logmel"] = {"ms": ms, "GBps_algorithmic": B * 2.688e6 / ms / 1e6}
+win = torch.hann_window(400, device=DEV)
+fb = filt
+
+
+def torch_mel():
+    st = torch.stft(audio, 400, 160, window=win, return_complex=True)
+    mag = st[..., :-1].abs() ** 2
+    lg = torch.clamp(fb @ mag, min=1e-10).log10()
+    lg = torch.maximum(lg, lg.amax(dim=(1, 2), keepdim=True) - 8.0)
+    return ((lg + 4.0) / 4.0).half()
+
+
+res["logmel"] = {"ms": ms, "GBps_algorithmic": B * 2.688e6 / ms / 1e6, "torch_stft_path_ms": timeit(torch_mel)}
+
+# VAD (Silero-class gate) over the same 64 x 30 s clips
+from whisperjav_b200.vad import VadB200  # noqa: E402
+vad = VadB200()
+ms = timeit(lambda: vad.probs(audio, ns))
+res["vad"] = {"ms": ms, "GBps_algorithmic": B * 1.92e6 / ms / 1e6, "windows": B * 938}
 print(json.dumps(res, indent=1))
 Path("gpurun_out").mkdir(exist_ok=True)
 Path("gpurun_out/perf_probe.json").write_text(json.dumps(res, indent=1))

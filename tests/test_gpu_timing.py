@@ -34,7 +34,10 @@ def clips():
     return [speech_shaped_audio(s, 1000 + i) for i, s in enumerate([30.0, 12.0, 5.0, 21.7])]
 
 
-def test_alignment_matrix_dtw_and_probs(tiny, clips, diag_dir):
+@pytest.mark.parametrize("mode", ["prefill", "steps"])
+def test_alignment_matrix_dtw_and_probs(tiny, clips, diag_dir, mode):
+    """Both forms of the teacher-forced pass -- every position a GEMM row (csrc/prefill.cu, the product default) and one position
+    per decode step through the step graph -- against the oracle."""
     dims, w, m, pw = tiny
     xa = m.encode(P.gpu_mel(m, clips))
     res = m.decode_features(xa, language="ja", max_initial_timestamp=0.0)
@@ -42,7 +45,7 @@ def test_alignment_matrix_dtw_and_probs(tiny, clips, diag_dir):
     text = [[t for t in r.tokens if t < tok.eot] for r in res]
     text[2] = []                                                  # a window without text is skipped
     frames = [min(3000, len(c) // 160) for c in clips]
-    got = m.align_windows(xa, text, frames, language="ja", return_matrix=True)
+    got = m.align_windows(xa, text, frames, language="ja", return_matrix=True, mode=mode)
     assert len(got[2][0]) == 0 and len(got[2][1]) == 0
     report = []
     for b in (0, 1, 3):
@@ -65,7 +68,24 @@ def test_alignment_matrix_dtw_and_probs(tiny, clips, diag_dir):
         assert dmat <= 2e-2, report[-1]
         assert close >= 0.9, report[-1]
         assert dp <= 0.15, report[-1]   # |d log p| = |d logit| up to a few fp16 quanta of a logit ~ 30
-    (diag_dir / "align_tiny.json").write_text(json.dumps(report))
+    (diag_dir / f"align_tiny_{mode}.json").write_text(json.dumps(report))
+
+
+def test_prefill_pass_equals_step_pass(tiny, clips):
+    """The two passes compute the same thing with different kernels (tcgen05 GEMM over all positions + prefill attention vs the
+    decode step graph): matrices agree to fp16 noise, DTW paths almost everywhere."""
+    dims, w, m, pw = tiny
+    xa = m.encode(P.gpu_mel(m, clips))
+    res = m.decode_features(xa, language="ja", max_initial_timestamp=0.0)
+    tok = M.Tokens(dims.n_vocab, "ja")
+    text = [[t for t in r.tokens if t < tok.eot] for r in res]
+    frames = [min(3000, len(c) // 160) for c in clips]
+    a = m.align_windows(xa, text, frames, language="ja", return_matrix=True, mode="prefill")
+    b = m.align_windows(xa, text, frames, language="ja", return_matrix=True, mode="steps")
+    for (ja, pa, ma), (jb, pb, mb) in zip(a, b):
+        assert ma.shape == mb.shape and float((ma - mb).abs().max()) <= 1e-2
+        assert np.mean(np.abs(ja - jb) <= 1) >= 0.95
+        assert np.max(np.abs(pa - pb) / (pb + 1e-4)) <= 0.1
 
 
 def test_transcribe_word_timestamps_matches_oracle(tiny, clips, diag_dir):

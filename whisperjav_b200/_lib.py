@@ -59,6 +59,9 @@ _SIGS = {
     "wjb_decode_set_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "wjb_align_qk_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "wjb_decode_set_align": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "wjb_align_prefill_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "wjb_align_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_size_t, C.c_void_p]),
     "wjb_align_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "wjb_align_dtw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

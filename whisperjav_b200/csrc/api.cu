@@ -88,6 +88,7 @@ struct ProfScope {
 int logmel_init();
 int vad_init();
 int align_init();
+int prefill_init();
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: run the kernel set-up once for every device a caller uses
 // (a process may hold one model per GPU).  Called at the top of every compute entry point, outside any stream capture.
@@ -104,6 +105,7 @@ int ensure_init() {
     if (int e = logmel_init()) return e;
     if (int e = vad_init()) return e;
     if (int e = align_init()) return e;
+    if (int e = prefill_init()) return e;
     if (dev < 64) done_mask |= 1ull << dev;
     return 0;
 }
@@ -570,6 +572,102 @@ int wjb_align_dtw(wjb_model* m, const void* qk, int batch, int n_steps, const in
     const wjb_dims& d = m->d;
     return launch_align(reinterpret_cast<const __half*>(qk), batch, (d.n_text_layer - d.n_text_layer / 2) * d.n_text_head, n_steps, d.n_audio_ctx,
                         n_tokens, row_begin, n_rows, n_frames2, medfilt_width, matrix, jump_frames, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- alignment, step 1 as ONE teacher-forced pass over whole sequences (every position a GEMM row)
+constexpr int kPrefillLogitRows = 4096;
+struct PfWs {
+    __half *x, *h, *qkv, *q, *a, *mlp, *logits;
+    size_t total;
+};
+static PfWs pf_ws(const wjb_dims& d, int R, uint8_t* base) {
+    PfWs w;
+    const size_t n = d.n_text_state;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        uint8_t* p = base ? base + off : nullptr;
+        off += al(bytes);
+        return reinterpret_cast<__half*>(p);
+    };
+    w.x = take((size_t)R * n * 2);
+    w.h = take((size_t)R * n * 2);
+    w.qkv = take((size_t)R * 3 * n * 2);
+    w.q = take((size_t)R * n * 2);
+    w.a = take((size_t)R * n * 2);
+    w.mlp = take((size_t)R * 4 * n * 2);
+    w.logits = take((size_t)(R < kPrefillLogitRows ? R : kPrefillLogitRows) * ((d.n_vocab + 63) & ~63) * 2);
+    w.total = off;
+    return w;
+}
+
+size_t wjb_align_prefill_workspace_bytes(const wjb_model* m, int batch, int n_steps) {
+    if (!m || batch <= 0 || n_steps <= 0) return 0;
+    return pf_ws(m->d, batch * n_steps, nullptr).total;
+}
+
+int wjb_align_prefill(wjb_model* m, const void* cross_kv, const int32_t* tokens, int tokens_stride, const int32_t* n_tokens, int batch, int n_steps,
+                      int eot, void* qk_out, float* token_prob_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!m || !cross_kv || !tokens || !n_tokens || !qk_out || !workspace) return set_error("align_prefill: null argument");
+    if (int e = ensure_init()) return e;
+    const wjb_dims& d = m->d;
+    const int n = d.n_text_state, H = d.n_text_head, T = d.n_audio_ctx, B = batch, Lp = n_steps, R = B * Lp;
+    if (Lp > d.n_text_ctx || Lp > 256) return set_error("align_prefill: %d positions (limit %d)", Lp, d.n_text_ctx < 256 ? d.n_text_ctx : 256);
+    if (tokens_stride < Lp) return set_error("align_prefill: tokens_stride < n_steps");
+    cudaStream_t s = (cudaStream_t)stream;
+    PfWs w = pf_ws(d, R, reinterpret_cast<uint8_t*>(workspace));
+    if (w.total > workspace_bytes) return set_error("align_prefill: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    auto linear = [&](const __half* A, int K, const __half* W, const __half* bias, const __half* res, __half* o, int N, int flags, int rows, long long ostride) {
+        GemmArgs q;
+        q.A = A;
+        q.a_row_stride = K;
+        q.rows_per_batch = rows;
+        q.n_batch = 1;
+        q.K = K;
+        q.W = W;
+        q.N = N;
+        q.ldw = K;
+        q.bias = bias;
+        q.residual = res;
+        q.out = o;
+        q.out_row_stride = ostride;
+        q.flags = flags;
+        return launch_gemm(q, s);
+    };
+    if (int e = launch_prefill_embed(tokens, tokens_stride, n_tokens, m->h16("dec.emb"), m->h16("dec.pos"), w.x, B, Lp, n, s)) return e;
+    const size_t cross_per_layer = (size_t)B * 2 * H * T * 64;
+    const int sel0 = d.n_text_layer / 2;
+    for (int i = 0; i < d.n_text_layer; ++i) {
+        const std::string p = "dec." + std::to_string(i) + ".";
+        if (int e = launch_layernorm(w.x, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"), w.h, R, n, s)) return e;
+        if (int e = linear(w.h, n, m->h16(p + "qkv.w"), m->h16(p + "qkv.b"), nullptr, w.qkv, 3 * n, 0, R, 3 * n)) return e;
+        if (int e = launch_prefill_self_attn(w.qkv, w.a, n_tokens, B, Lp, H, s)) return e;
+        if (int e = linear(w.a, n, m->h16(p + "out.w"), m->h16(p + "out.b"), w.x, w.x, n, 0, R, n)) return e;
+        if (int e = launch_layernorm(w.x, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"), w.h, R, n, s)) return e;
+        if (int e = linear(w.h, n, m->h16(p + "cq.w"), m->h16(p + "cq.b"), nullptr, w.q, n, 0, R, n)) return e;
+        CrossCapture cap;
+        if (i >= sel0) {
+            cap.base = reinterpret_cast<__half*>(qk_out) + (long long)(i - sel0) * H * Lp * T;
+            cap.b_stride = (long long)(d.n_text_layer - sel0) * H * Lp * T;
+            cap.head_stride = (long long)Lp * T;
+        }
+        if (int e = launch_prefill_cross_attn(w.q, reinterpret_cast<const __half*>(cross_kv) + i * cross_per_layer, w.a, n_tokens, B, Lp, H, T,
+                                              cap.base ? &cap : nullptr, s))
+            return e;
+        if (int e = linear(w.a, n, m->h16(p + "cout.w"), m->h16(p + "cout.b"), w.x, w.x, n, 0, R, n)) return e;
+        if (int e = launch_layernorm(w.x, m->h16(p + "ln3.g"), m->h16(p + "ln3.b"), w.h, R, n, s)) return e;
+        if (int e = linear(w.h, n, m->h16(p + "fc1.w"), m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, GEMM_GELU, R, 4 * n)) return e;
+        if (int e = linear(w.mlp, 4 * n, m->h16(p + "fc2.w"), m->h16(p + "fc2.b"), w.x, w.x, n, 0, R, n)) return e;
+    }
+    if (token_prob_out) {
+        if (int e = launch_layernorm(w.x, m->h16("dec.ln.g"), m->h16("dec.ln.b"), w.h, R, n, s)) return e;
+        const int ls = (d.n_vocab + 63) & ~63;
+        for (int r0 = 0; r0 < R; r0 += kPrefillLogitRows) {
+            const int rows = R - r0 < kPrefillLogitRows ? R - r0 : kPrefillLogitRows;
+            if (int e = linear(w.h + (size_t)r0 * n, n, m->h16("dec.emb"), nullptr, nullptr, w.logits, d.n_vocab, 0, rows, ls)) return e;
+            if (int e = launch_prefill_prob(w.logits, ls, r0, rows, tokens, tokens_stride, n_tokens, token_prob_out, Lp, eot, s)) return e;
+        }
+    }
+    return 0;
 }
 
 // The kernels of one decoder step for B rows on stream s (captured into the step graph).

@@ -193,6 +193,15 @@ size_t align_workspace_bytes(int B, int n_sel, int n_steps, int T);
 int launch_align(const __half* qk, int B, int n_sel, int n_steps, int T, const int* n_tok, const int* row_begin, const int* n_rows,
                  const int* n_frames2, int medfilt, float* matrix, int* jump, void* workspace, size_t ws_bytes, cudaStream_t s);
 
+// ---- teacher-forced pass over whole sequences (prefill.cu) ---------------------------------------
+int launch_prefill_embed(const int* tokens, int tok_stride, const int* n_tok, const __half* emb, const __half* pos, __half* x, int B, int Lp, int n,
+                         cudaStream_t s);
+int launch_prefill_self_attn(const __half* qkv, __half* out, const int* n_tok, int B, int Lp, int H, cudaStream_t s);
+int launch_prefill_cross_attn(const __half* q, const __half* kv, __half* out, const int* n_tok, int B, int Lp, int H, int T, const CrossCapture* cap,
+                              cudaStream_t s);
+int launch_prefill_prob(const __half* logits, int stride, int r0, int rows, const int* tokens, int tok_stride, const int* n_tok, float* prob, int Lp,
+                        int eot, cudaStream_t s);
+
 // ---- VAD (vad.cu) --------------------------------------------------------------------------
 struct VadArgs;
 }  // namespace wjb

@@ -383,11 +383,14 @@ class WhisperB200:
         return res, trace
 
     def align_windows(self, xa: torch.Tensor, text_tokens: Sequence[Sequence[int]], num_frames: Sequence[int], *, language="ja",
-                      task="transcribe", medfilt_width: int = 7, return_matrix: bool = False):
+                      task="transcribe", medfilt_width: int = 7, return_matrix: bool = False, mode: str = "prefill"):
         """timing.py::find_alignment for B windows in one device pass (wjb_decode_set_align + wjb_align_dtw): the decoder is
         teacher-forced over [sot sequence, <|notimestamps|>, text tokens, <|endoftext|>], the cross-attention scores of the
         alignment heads are captured, turned into the token x frame matrix and aligned by DTW.  Per window returns
-        (jump_frames int array [n_text + 1], token_probs float array [n_text]); windows without text tokens get empty arrays."""
+        (jump_frames int array [n_text + 1], token_probs float array [n_text]); windows without text tokens get empty arrays.
+        ``mode``: "prefill" = one pass with every position a GEMM row (``wjb_align_prefill``: one sweep of the decoder weights);
+        "steps" = the same arithmetic through the decode step graph, one position per step (``wjb_decode_set_align``; kept as
+        the cross-check of the prefill kernels, tests/test_gpu_timing.py)."""
         d = self.dims
         B = xa.shape[0]
         tok = Tokens(d.n_vocab, language, task)
@@ -401,7 +404,7 @@ class WhisperB200:
         if len(live) < B:
             sub = self.align_windows(xa[torch.tensor(live, device=self.device)].contiguous(), [text_tokens[b] for b in live],
                                      [num_frames[b] for b in live], language=language, task=task, medfilt_width=medfilt_width,
-                                     return_matrix=return_matrix)
+                                     return_matrix=return_matrix, mode=mode)
             out = [empty + ((None,) if return_matrix else ())] * B
             for b, r in zip(live, sub):
                 out[b] = r
@@ -409,6 +412,10 @@ class WhisperB200:
         max_len = max(len(q) for q in seqs)
         if max_len > d.n_text_ctx:
             raise ValueError("alignment sequence longer than n_text_ctx")
+        if mode == "prefill" and max_len <= 256:
+            max_len = (max_len + 7) // 8 * 8  # padded row count per window
+        else:
+            mode = "steps"
         sample_len = max_len - n_initial + 1
         stride = n_initial + sample_len + 1
         opts = _lib.DecodeOpts()
@@ -437,15 +444,21 @@ class WhisperB200:
             slp = torch.zeros(3, B, dtype=torch.float32, device=dev)
             olen = torch.zeros(B, dtype=torch.int32, device=dev)
             steps = C.c_int(0)
-            _lib.check(self.lib.wjb_decode_set_trace(self._h, None, 0, None, _lib.ptr(forced)), "wjb_decode_set_trace")
-            _lib.check(self.lib.wjb_decode_set_align(self._h, _lib.ptr(qk), max_len, _lib.ptr(n_tok), _lib.ptr(prob)), "wjb_decode_set_align")
-            try:
-                _lib.check(self.lib.wjb_decode_greedy(self._h, _lib.ptr(kv), B, C.byref(opts), None, _lib.ptr(tokens), _lib.ptr(slp[0]),
-                                                     _lib.ptr(slp[1]), _lib.ptr(olen), _lib.ptr(ws), ws_bytes, C.byref(steps),
-                                                     _lib.stream_ptr()), "wjb_decode_greedy (alignment pass)")
-            finally:
-                self.lib.wjb_decode_set_align(self._h, None, 0, None, None)
-                self.lib.wjb_decode_set_trace(self._h, None, 0, None, None)
+            if mode == "prefill":
+                pws_bytes = self.lib.wjb_align_prefill_workspace_bytes(self._h, B, max_len)
+                pws = self._buf("align_pf_ws", pws_bytes)
+                _lib.check(self.lib.wjb_align_prefill(self._h, _lib.ptr(kv), _lib.ptr(forced), stride, _lib.ptr(n_tok), B, max_len, tok.eot, _lib.ptr(qk),
+                                                     _lib.ptr(prob), _lib.ptr(pws), pws_bytes, _lib.stream_ptr()), "wjb_align_prefill")
+            else:
+                _lib.check(self.lib.wjb_decode_set_trace(self._h, None, 0, None, _lib.ptr(forced)), "wjb_decode_set_trace")
+                _lib.check(self.lib.wjb_decode_set_align(self._h, _lib.ptr(qk), max_len, _lib.ptr(n_tok), _lib.ptr(prob)), "wjb_decode_set_align")
+                try:
+                    _lib.check(self.lib.wjb_decode_greedy(self._h, _lib.ptr(kv), B, C.byref(opts), None, _lib.ptr(tokens), _lib.ptr(slp[0]),
+                                                         _lib.ptr(slp[1]), _lib.ptr(olen), _lib.ptr(ws), ws_bytes, C.byref(steps),
+                                                         _lib.stream_ptr()), "wjb_decode_greedy (alignment pass)")
+                finally:
+                    self.lib.wjb_decode_set_align(self._h, None, 0, None, None)
+                    self.lib.wjb_decode_set_trace(self._h, None, 0, None, None)
             matrix = torch.zeros(B, max_len, d.n_audio_ctx, dtype=torch.float32, device=dev)
             jump = torch.zeros(B, max_len, dtype=torch.int32, device=dev)
             aws_bytes = self.lib.wjb_align_workspace_bytes(self._h, B, max_len)
