@@ -367,7 +367,7 @@ def parity_check(m, model_name, clips, dec_kw, sample_len=40):
     mel = P.gpu_mel(m, clips)
     mel_err = float((mel[:, 1:-1].permute(0, 2, 1).float().cpu() - P.oracle_mel_windows(clips, dims)).abs().max())
     enc, xa = P.encoder_parity(m, w, dims, mel, prepared=pw)
-    rep = P.decode_parity(m, w, dims, xa, prepared=pw, sample_len=sample_len, tie_quanta=8.0, logit_quanta=32.0, logit_rms_quanta=6.0, **dec_kw)
+    rep = P.decode_parity(m, w, dims, xa, prepared=pw, sample_len=sample_len, tie_quanta=8.0, logit_quanta=40.0, logit_rms_quanta=8.0, logprob_tol_per_step=0.06, **dec_kw)
     ok = bool(rep["ok"] and enc["ok"] and mel_err <= 1e-3)
     return {"ok": ok, "windows": rep["windows"], "steps_checked": rep["steps_checked"], "identical_windows": rep["identical_windows"],
             "tie_breaks": rep["tie_breaks"], "dlogit_quanta_max": rep["dlogit_quanta_max"], "tolerances": rep["tolerances"],

@@ -36,7 +36,7 @@ def fp16_quantum(x: float) -> float:
 
 
 def decode_parity(model, weights, dims, xa: torch.Tensor, *, tie_quanta: float = 4.0, logit_quanta: float = 16.0,
-                  logit_rms_quanta: float = 3.0, prepared=None, **decode_kw) -> Dict:
+                  logit_rms_quanta: float = 3.0, logprob_tol_per_step: float = 0.02, prepared=None, **decode_kw) -> Dict:
     """Greedy decode of encoder output ``xa`` (device tensor) on the GPU vs the oracle.  ``decode_kw`` are DecodingOptions
     fields understood by both sides (language, without_timestamps, max_initial_timestamp, sample_len, suppress_tokens ...).
     Returns a report dict; ``report["ok"]`` is the verdict, ``report["failures"]`` says why not."""
@@ -88,7 +88,7 @@ def decode_parity(model, weights, dims, xa: torch.Tensor, *, tie_quanta: float =
         for t in ties:
             if t["gap_quanta"] > tie_quanta:
                 failures.append({"b": b, "why": "device token is not a near-tie of the oracle's arg-max", **t})
-        if abs(res[b].sum_logprob - ref[b].sum_logprob) > 0.02 * max(1, n_steps):
+        if abs(res[b].sum_logprob - ref[b].sum_logprob) > logprob_tol_per_step * max(1, n_steps):
             failures.append({"b": b, "why": "sum_logprob", "gpu": res[b].sum_logprob, "oracle": ref[b].sum_logprob})
         if abs(res[b].no_speech_prob - ref[b].no_speech_prob) > 1e-3 + 0.03 * ref[b].no_speech_prob:
             failures.append({"b": b, "why": "no_speech_prob", "gpu": res[b].no_speech_prob, "oracle": ref[b].no_speech_prob})

@@ -6,7 +6,7 @@ Same checker as the tiny tests (oracle/parity.py) on the large-v3 synthetic weig
         8 / 16 / 24 / 32 (residual-stream taps, ``wjb_encoder_set_tap``);
   (iii) cross-attention K/V of every layer vs the oracle's Linear on the same encoder output;
   (iv)  decode in both timestamp modes: every step's raw logits vs the oracle teacher-forced along the device's sequence
-        (max over the vocabulary <= 32 fp16 quanta, rms <= 6), every device token the oracle's arg-max on that prefix or a counted
+        (max over the vocabulary <= 40 fp16 quanta, rms <= 8), every device token the oracle's arg-max on that prefix or a counted
         near-tie (<= 8 quanta), the
         large-v3 special-token ids (timestamp_begin 50365 ...) exercised through the filters.
 
@@ -87,10 +87,10 @@ def test_decode_logits_and_tokens(large, encoded, diag_dir, without_timestamps):
     dims, w, m, pw = large
     _, _, xa = encoded
     # tolerances: a 32-layer random-init decoder amplifies a perturbation of fp16-rounding size (3e-4 relative on the encoder
-    # output) to ~10 quanta of logit difference by itself (scripts/synth_chaos.py: max 9.5, median 6.5 over 64 steps with this
-    # preset; the 4-layer tiny model: 8 / 4), so the bounds are twice the tiny ones
+    # output) to ~20 quanta of logit difference by itself (scripts/synth_chaos.py: max 19, median 9 over 45 steps with this
+    # preset; the 4-layer tiny model: 8 / 4), so the bounds are 2.5 x the tiny ones
     rep = P.decode_parity(m, w, dims, xa, prepared=pw, language="ja", without_timestamps=without_timestamps, max_initial_timestamp=0.0,
-                          sample_len=SAMPLE_LEN, tie_quanta=8.0, logit_quanta=32.0, logit_rms_quanta=6.0)
+                          sample_len=SAMPLE_LEN, tie_quanta=8.0, logit_quanta=40.0, logit_rms_quanta=8.0, logprob_tol_per_step=0.06)
     (diag_dir / f"tokens_large_v3_wt{int(without_timestamps)}.json").write_text(json.dumps(rep, indent=1))
     assert rep["ok"], rep["failures"]
     assert rep["steps_checked"] >= N_WIN * 8

@@ -457,13 +457,6 @@ static unsigned long long* g_trace = nullptr;
 void gemm_set_trace(void* buf) { g_trace = reinterpret_cast<unsigned long long*>(buf); }
 
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
-    {
-        static bool inited = false;
-        if (!inited) {
-            if (int e = gemm_init()) return e;
-            inited = true;
-        }
-    }
     if ((a.bias || a.residual || a.pos) && (a.N % 32)) return set_error("gemm: bias/residual/pos need N %% 32 == 0");
     if (a.K % 8 != 0 || a.ldw % 8 != 0) return set_error("gemm: K and ldw must be multiples of 8 (16-byte TMA rows)");
     if ((a.a_row_stride % 8) || (a.a_batch_stride % 8)) return set_error("gemm: A strides must be multiples of 8 halfs");

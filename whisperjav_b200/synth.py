@@ -60,7 +60,7 @@ def _sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> to
 # scripts/synth_stats.py, CPU oracle) so that greedy sequences end at varied lengths in both timestamp modes.
 SYNTH_PRESETS = {
     "tiny": {"seed": 5},
-    "large-v3": {"seed": 11, "eot_boost": 4.0, "attn_logit_std": 5.0, "cross_attn_logit_std": 12.0, "cross_gain": 0.25},
+    "large-v3": {"seed": 11, "eot_boost": 4.0, "attn_logit_std": 6.0, "cross_attn_logit_std": 14.0, "cross_gain": 0.3},
 }
 
 
