@@ -158,3 +158,71 @@ def test_host_finalize_and_ranker_agree_with_the_oracle():
         sel = wo.rank_maximum_likelihood(cand, sums, lp)[0]
         assert ids == cand[0][sel].tolist(), (trial, finished, live_tok, live_sum)
         assert score == pytest.approx(sums[0][sel])
+
+
+def _toy_logits(prefix, V):
+    """A deterministic 'language model' on a toy vocabulary: logits depend on the whole prefix."""
+    g = torch.Generator().manual_seed(hash(tuple(prefix)) % (2 ** 31))
+    return torch.randn(V, generator=g) * 2.0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_beam_search_is_exhaustive_search_when_the_beam_holds_every_prefix(seed):
+    """BeamSearch.update / finalize / ranker pinned against brute force: on a toy vocabulary (V = 4 + eot) and horizon 2 a beam of 4
+    prunes nothing at step 1 (4 live prefixes), so (a) after every step the live set must be exactly the top-`beam` of ALL
+    non-eot prefixes of that length by cumulative log-probability (here: all of them while they fit), (b) every eot-terminated
+    sequence of the best `max_candidates` found on the way must carry its exact brute-force score, and (c) the finished list the
+    search ends with must be the best `max_candidates` complete hypotheses a brute-force enumeration finds under the same
+    "finish when the candidate list is full" rule applied step by step."""
+    V, eot, horizon = 5, 4, 2
+    beam = 4                       # 4 live prefixes after step 1: every length-2 prefix extends a kept one
+    torch.manual_seed(seed)
+    prompt = [int(torch.randint(0, 4, (1,)))]
+    bs = wo.BeamSearch(beam_size=beam, eot=eot, patience=16.0)    # 64 candidates: the list never fills before the horizon
+    tokens = torch.tensor([prompt] * beam)
+    slp = torch.zeros(beam)
+    # brute force: cumulative log-prob of every sequence
+    def score(seq):
+        s, p = 0.0, list(prompt)
+        for t in seq:
+            s += torch.log_softmax(_toy_logits(p, V), -1)[t].item()
+            p.append(t)
+        return s
+    import itertools
+    finished_expected = {}
+    kept_prev = []
+    for step in range(horizon):
+        logits = torch.stack([_toy_logits(tokens[r].tolist(), V) for r in range(beam)])
+        tokens, src, completed = bs.update(tokens, logits, slp)
+        live = {tuple(t.tolist()[len(prompt):]) for t in tokens}
+        # all non-eot sequences of this length (identical beams collapse, so the live set is a set of distinct prefixes)
+        every = [s for s in itertools.product(range(4), repeat=step + 1)]
+        best = sorted(every, key=lambda s: -score(s))[:beam]
+        assert live == set(best), (step, live ^ set(best))
+        for r in range(len(tokens)):  # cumulative scores carried with the rows
+            assert slp[r].item() == pytest.approx(score(tuple(tokens[r].tolist()[len(prompt):])), abs=1e-5)
+        # eot-terminated candidates finish only if they rank above the beam-th live candidate of their step
+        cands = [p + (t,) for p in (kept_prev if step else [()]) for t in range(V)]
+        n_live = 0
+        for c in sorted(cands, key=lambda c: -score(c)):
+            if c[-1] == eot:
+                finished_expected[tuple(prompt) + c] = score(c)
+            else:
+                n_live += 1
+                if n_live == beam:
+                    break
+        kept_prev = sorted(live)
+        # pad the rows back to `beam` (upstream keeps exactly beam rows; duplicates collapse in the next update)
+        if len(tokens) < beam:
+            reps = (beam + len(tokens) - 1) // len(tokens)
+            slp = slp[: len(tokens)].repeat(reps)[:beam].clone()
+            tokens = tokens.repeat(reps, 1)[:beam]
+    fin = bs.finished_sequences[0]
+    assert set(fin) == set(finished_expected)                        # every eot-terminated hypothesis was found ...
+    for k, v in fin.items():
+        assert v == pytest.approx(finished_expected[k], abs=1e-5)    # ... with its exact score
+    toks, sums = bs.finalize(tokens.view(1, beam, -1), slp.view(1, beam))
+    pick = wo.rank_maximum_likelihood(toks, sums)[0]
+    cands = {tuple(t.tolist()): s for t, s in zip(toks[0], sums[0])}
+    best_seq = max(cands, key=lambda k: cands[k] / len(k))
+    assert tuple(toks[0][pick].tolist()) == best_seq
