@@ -506,7 +506,8 @@ def run_stream(args):
     from whisperjav_b200.audioio import compose_srt
     from whisperjav_b200.distributed import gather_segment_records, pack_records
     from whisperjav_b200.segmenter import B200SpeechSegmenter
-    from whisperjav_b200.synth import speech_shaped_stream
+    from whisperjav_b200.scenes import B200SceneDetector
+    from whisperjav_b200.synth import film_audio
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -534,7 +535,8 @@ def run_stream(args):
             decode.pop(k, None)
     if args.word_timestamps:
         decode["word_timestamps"] = True
-    streams = [speech_shaped_stream(seconds, (4000 if anime else 3000) + k) for k in range(n_streams)]
+    streams = [film_audio(seconds, (4000 if anime else 3000) + k) for k in range(n_streams)]
+    scene_det = B200SceneDetector(device=f"cuda:{local}")   # reference defaults: 29 s scenes, 32 / 38 dB gates, 1.8 / 0.94 s silences
     sync = torch.cuda.synchronize
 
     def barrier():
@@ -545,13 +547,13 @@ def run_stream(args):
 
     def run(strs):
         if world > 1:
-            r = S.transcribe_streams_distributed(m, seg, strs, decode=decode, sync=sync, device=f"cuda:{local}")
+            r = S.transcribe_streams_distributed(m, seg, strs, decode=decode, sync=sync, device=f"cuda:{local}", scene_detector=scene_det)
             rec = pack_records([(s_["stream"] * 10_000_000 + int(s_["start"] * 100), s_["start"], s_["end"], s_["avg_logprob"], s_["no_speech_prob"],
                                  s_["tokens"]) for s_ in r.segments])
             allr = gather_segment_records(rec, device=f"cuda:{local}")
             srt = compose_srt([{"start": x["start"], "end": x["end"], "text": M.detokenize([t for t in x["tokens"] if t < 50257])} for x in allr]) if rank == 0 else ""
         else:
-            r = S.transcribe_streams(m, seg, strs, decode=decode, sync=sync)
+            r = S.transcribe_streams(m, seg, strs, decode=decode, sync=sync, scene_detector=scene_det)
             srt = compose_srt(r.segments)
         return r, srt
 
@@ -570,7 +572,8 @@ def run_stream(args):
     wall = time.perf_counter() - t0
     dev_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([dev_ms, r.stages_s["vad"] * 1e3, r.stages_s["transcribe"] * 1e3, wall * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, r.stages_s["vad"] * 1e3, r.stages_s["transcribe"] * 1e3, wall * 1e3, r.stages_s["scenes"] * 1e3], dtype=torch.float64,
+                     device="cuda")
     tmax, tsum = t.clone(), t.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -582,14 +585,15 @@ def run_stream(args):
             "metric": f"audio-seconds/sec (RTFx) {'anime-shaped: TEN-style VAD + greedy decode, 8 streams' if anime else 'balanced-shaped: VAD + mel + large-v3 transcribe, 1 stream'}",
             "value": audio_s / (total_ms / 1e3), "unit": "audio-s/s", "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": total_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
-            "data": "synthetic (speech-shaped 16 kHz streams assembled from 40 seeded 30 s clips; seeded random-init weights)",
-            "config": {"workload": f"BASELINE config {'4' if anime else '3'}: {n_streams} x {args.stream_minutes} min stream(s) -> 29 s scenes -> b200-vad -> groups "
+            "data": "synthetic (film-shaped 16 kHz streams: chapters of seeded speech-shaped clips, room-tone gaps, in-chapter pauses; seeded random-init weights)",
+            "config": {"workload": f"BASELINE config {'4' if anime else '3'}: {n_streams} x {args.stream_minutes} min stream(s) -> b200-auditok scenes (<= 29 s) -> b200-vad -> groups "
                                    f"({'chunk 0.5 s / max 5 s' if anime else 'balanced preset: chunk 2.5 s / max 6 s'}) -> transcribe_batch (batch {args.batch}, decode {args.decode or "preset"}"
                                    f"{'' if anime else ', timestamps on, thresholds on'}) -> segments -> SRT text; host audio in, host text out",
                        "decode": {k: v for k, v in decode.items()}, "parallelism": f"units dealt over {world} rank(s) by speech seconds"},
             "e2e": {"value": audio_s / (total_ms / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": int(audio_s * 16000 * 4 + r.stats["unit_audio_s"] * world * 16000 * 4),
                     "d2h_bytes_per_step": int(r.stats["units"] * world * 240 * 4), "api": "stream.transcribe_streams(host fp32 streams) -> segments -> SRT"},
-            "stages_ms_max_over_ranks": {"vad": float(tmax[1]), "transcribe": float(tmax[2]), "wall": float(tmax[3])},
+            "stages_ms_max_over_ranks": {"scenes": float(tmax[4]), "vad": float(tmax[1]), "transcribe": float(tmax[2]), "wall": float(tmax[3])},
+            "scenes_rank0": r.stats["scenes"],
             "straggler_ratio": float(tmax[0] / (tsum[0] / world)),
             "units_total": r.stats["units_total"], "units_rank0": r.stats["units"], "speech_s_rank0": r.stats["speech_s"],
             "windows_rank0": m.stats["windows"] - p0["windows"], "decoder_steps_rank0": m.stats["decode_steps"] - p0["decode_steps"],

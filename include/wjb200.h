@@ -235,6 +235,20 @@ int wjb_vad_forward(const float* audio, int64_t audio_stride, const int32_t* n_s
  * frames x fp16 [rows][n]; the encoder itself is wjb_encoder_forward on a base-sized model handle. */
 int wjb_frame_head_f16(const void* x, const void* w, float bias, float* prob, int rows, int n, void* stream);
 
+/* ---- scene-detection energy gate ------------------------------------------------------------------
+ * Replaces the per-block energy computation inside `auditok.split(audio_bytes, ..., energy_threshold=...)` at
+ * modules/scene_detection_backends/auditok_backend.py:392 (pass 1, the whole stream) and :567 (pass 2, every oversized
+ * chapter) [auditok 0.3.0 `signal.calculate_energy` on 50 ms blocks of the int16 bytes built by
+ * `(audio * 32767).astype(np.int16)` at :379 / :555].
+ *   audio         fp32 [n_audio] mono samples of the stream
+ *   region_start / region_len  int64 [n_regions]: sample range of every region of this pass (pass 1: one region = the stream)
+ *   window_base   int64 [n_regions + 1]: windows before region r (window_base[n_regions] = n_windows); region r has
+ *                 ceil(region_len[r] / window) windows, the last one may be short
+ *   sumsq         uint64 [n_windows]: EXACT sum over the window of (int16 sample)^2 -- the host derives upstream's float64 dB
+ *                 value and the `>= energy_threshold` flag from it bit-identically (whisperjav_b200/scenes.py). */
+int wjb_scene_energy(const float* audio, int64_t n_audio, const int64_t* region_start, const int64_t* region_len,
+                     const int64_t* window_base, int n_regions, int window, uint64_t* sumsq, int64_t n_windows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

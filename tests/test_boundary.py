@@ -72,11 +72,21 @@ def test_wav_and_srt_io(tmp_path):
 
 
 @pytest.mark.skipif(not Path("/root/reference/whisperjav").exists(), reason="reference tree not present (GPU box)")
-def test_registration_with_reference_factories():
+def test_registration_with_reference_factories(monkeypatch):
+    import types
     sys.path.insert(0, "/root/reference")
+    for absent in ("librosa", "soundfile"):  # imported at module level by scene_detection_backends/utils.py, not installed here
+        if absent not in sys.modules:
+            monkeypatch.setitem(sys.modules, absent, types.ModuleType(absent))
     try:
         done = whisperjav_b200.register()
-        assert done == {"speech_segmenter": True, "text_generator": True}
+        assert done == {"speech_segmenter": True, "text_generator": True, "scene_detector": True}
+        from whisperjav.modules.scene_detection_backends.base import SceneDetector
+        from whisperjav.modules.scene_detection_backends.factory import SceneDetectorFactory
+        det = SceneDetectorFactory.create("b200-auditok", max_duration=20.0, pass2_max_silence_s=0.5)
+        assert isinstance(det, SceneDetector) and det.name == "b200-auditok"
+        assert det._config.max_duration == 20.0 and det._config.pass2_max_duration == 19.0 and det._config.pass2_max_silence == 0.5
+        assert SceneDetectorFactory.is_backend_available("b200-auditok") == (True, "")
         from whisperjav.modules.speech_segmentation import SpeechSegmenterFactory
         from whisperjav.modules.speech_segmentation.base import SpeechSegmenter
         from whisperjav.modules.subtitle_pipeline.generators.factory import TextGeneratorFactory

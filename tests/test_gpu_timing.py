@@ -84,8 +84,16 @@ def test_prefill_pass_equals_step_pass(tiny, clips):
     a = m.align_windows(xa, text, frames, language="ja", return_matrix=True, mode="prefill")
     b = m.align_windows(xa, text, frames, language="ja", return_matrix=True, mode="steps")
     for (ja, pa, ma), (jb, pb, mb) in zip(a, b):
-        assert ma.shape == mb.shape and float((ma - mb).abs().max()) <= 1e-2
-        assert np.mean(np.abs(ja - jb) <= 1) >= 0.95
+        dmax = float((ma - mb).abs().max())
+        assert ma.shape == mb.shape and dmax <= 1e-2
+        # DTW is an arg-min over paths of a near-flat matrix (random model): a 1e-2 perturbation may move a stretch of the path
+        # (same caveat as the oracle comparison above), so besides the jump frames the check is near-optimality: the prefill
+        # pass's path, costed on the step pass's matrix, is within the bound the matrix difference allows of that matrix's optimum
+        xa_, xb_ = -ma.double().numpy(), -mb.double().numpy()
+        (ta, fa), (tb, fb) = to.dtw(xa_), to.dtw(xb_)
+        gap = float(xb_[ta, fa].sum() - xb_[tb, fb].sum())
+        assert -1e-9 <= gap <= 2 * max(len(ta), len(tb)) * dmax + 1e-9, (gap, dmax)
+        assert np.mean(np.abs(ja - jb) <= 1) >= 0.75
         assert np.max(np.abs(pa - pb) / (pb + 1e-4)) <= 0.1
 
 

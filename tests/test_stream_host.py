@@ -66,7 +66,7 @@ def test_units_offsets_and_filter():
     a = make_stream(1)
     m, seg = FakeModel(), FakeSegmenter()
     r = S.transcribe_streams(m, seg, [a], decode=dict(S.BALANCED_DECODE))
-    assert r.stats["units"] == len(r.units) > 5 and set(r.stages_s) == {"vad", "transcribe", "total"}
+    assert r.stats["units"] == len(r.units) > 5 and set(r.stages_s) == {"scenes", "vad", "transcribe", "total"}
     for u in r.units:
         assert np.all(np.abs(a[u.start_sample: u.end_sample][[1, -2]]) > 0.5)        # starts / ends on speech (int(sec * sr) slicing as whisper_pro_asr.py:381)
         assert (u.end_sample - u.start_sample) / SR <= 6.0 + 3.0 + 1e-6                 # group rule: <= max_group + one segment

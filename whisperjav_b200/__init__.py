@@ -11,7 +11,7 @@ __version__ = "0.1.0"
 
 def register() -> dict:
     """Returns {surface: registered?}.  Safe to call when WhisperJAV is not installed."""
-    done = {"speech_segmenter": False, "text_generator": False}
+    done = {"speech_segmenter": False, "text_generator": False, "scene_detector": False}
     try:
         from whisperjav.modules.speech_segmentation import factory as sf  # type: ignore
         sf._BACKEND_REGISTRY["b200-vad"] = "whisperjav_b200.segmenter.B200SpeechSegmenter"
@@ -25,6 +25,13 @@ def register() -> dict:
         from whisperjav.modules.subtitle_pipeline.generators import factory as gf  # type: ignore
         gf._REGISTRY["b200-whisper"] = "whisperjav_b200.generator.B200WhisperGenerator"
         done["text_generator"] = True
+    except Exception:
+        pass
+    try:
+        from whisperjav.modules.scene_detection_backends import factory as scf  # type: ignore
+        scf._BACKEND_REGISTRY["b200-auditok"] = "whisperjav_b200.scenes.B200SceneDetector"
+        scf._BACKEND_DEPENDENCIES["b200-auditok"] = {"packages": [], "install_hint": "", "always_available": True}
+        done["scene_detector"] = True
     except Exception:
         pass
     return done

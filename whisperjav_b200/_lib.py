@@ -88,6 +88,7 @@ _SIGS = {
     "wjb_vad_weights_bytes": (C.c_size_t, []),
     "wjb_vad_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "wjb_vad_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "wjb_scene_energy": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS)

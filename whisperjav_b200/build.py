@@ -15,7 +15,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "libwjb200.so"
-SOURCES = ["api.cu", "gemm_tc.cu", "gemm_step.cu", "attention.cu", "elementwise.cu", "logmel.cu", "decode.cu", "align.cu", "prefill.cu", "vad.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "gemm_step.cu", "attention.cu", "elementwise.cu", "logmel.cu", "decode.cu", "align.cu", "prefill.cu", "vad.cu", "scene.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

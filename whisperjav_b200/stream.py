@@ -4,8 +4,9 @@ This is the per-scene loop of the reference's balanced / fidelity pipelines (``f
 whisperjav/pipelines/fidelity_pipeline.py:348, balanced_pipeline.py:483) and the per-group loop inside the ASR wrapper
 (whisperjav/modules/whisper_pro_asr.py:306-314) flattened into device batches:
 
-* the stream is cut into scenes (the scene detector is upstream of the path and not replaced; a fixed-length cut at
-  ``scene_s`` stands in for its output -- SURVEY.md 8b B5);
+* the stream is cut into scenes: by the two-pass silence detector with its energy gate on the device
+  (``scenes.B200SceneDetector.detect``, one kernel launch per pass over the whole stream -- auditok_backend.py:229-567) when a
+  ``scene_detector`` is given, else by a fixed-length cut at ``scene_s``;
 * every scene goes through the VAD gate in ONE device pass (``B200SpeechSegmenter.segment_batch``) instead of one CPU model
   call per window per scene; VAD sanity fall-back as whisper_pro_asr.py:262-300 (``hostlogic.vad_looks_broken``);
 * every VAD group of every scene becomes one clip of ONE ``transcribe_batch`` call (``max_batch`` windows per device pass, longest
@@ -66,15 +67,27 @@ def cut_scenes(n_samples: int, scene_s: float = 29.0) -> List[Tuple[int, int]]:
     return [(a, min(a + step, n_samples)) for a in range(0, n_samples, step)]
 
 
+def detect_scene_cuts(audio: np.ndarray, scene_detector) -> List[Tuple[int, int]]:
+    """Sample ranges of the detector's scenes (the slices ``save_scene_wav`` would write, auditok_backend.py:440-441)."""
+    scenes, _, _ = scene_detector.detect(audio, SR)
+    cuts = [(int(s.start_sec * SR), int(s.end_sec * SR)) for s in scenes]
+    return [(a, b) for a, b in cuts if b > a]
+
+
 def vad_units(segmenter, streams: Sequence[np.ndarray], scene_s: float = 29.0, scene_batch: int = 256,
-              stream_ids: Optional[Sequence[int]] = None) -> List[Unit]:
+              stream_ids: Optional[Sequence[int]] = None, scene_detector=None, timing: Optional[Dict[str, float]] = None) -> List[Unit]:
     """Scenes of every stream through the VAD gate (``scene_batch`` scenes per device pass) -> one Unit per VAD group."""
     units: List[Unit] = []
     todo = []
+    t0 = time.perf_counter()
     for k, audio in enumerate(streams):
         sid = stream_ids[k] if stream_ids is not None else k
-        for j, (a, b) in enumerate(cut_scenes(len(audio), scene_s)):
+        cuts = cut_scenes(len(audio), scene_s) if scene_detector is None else detect_scene_cuts(audio, scene_detector)
+        for j, (a, b) in enumerate(cuts):
             todo.append((sid, j, a, b, audio))
+    if timing is not None:
+        timing["scenes"] = time.perf_counter() - t0
+        timing["n_scenes"] = len(todo)
     for c0 in range(0, len(todo), scene_batch):
         chunk = todo[c0: c0 + scene_batch]
         results = segmenter.segment_batch([aud[a:b] for (_, _, a, b, aud) in chunk], sample_rate=SR)
@@ -118,19 +131,21 @@ def transcribe_units(model, streams: Dict[int, np.ndarray], units: Sequence[Unit
 
 
 def transcribe_streams(model, segmenter, streams: Sequence[np.ndarray], decode: Optional[dict] = None, scene_s: float = 29.0,
-                       sync=None) -> StreamResult:
+                       sync=None, scene_detector=None) -> StreamResult:
     """The whole path for a list of streams on one GPU.  ``sync`` (e.g. torch.cuda.synchronize) is called at the stage
     boundaries so the per-stage wall times are attributable."""
     decode = dict(BALANCED_DECODE if decode is None else decode)
     t0 = time.perf_counter()
-    units = vad_units(segmenter, streams, scene_s)
+    timing: Dict[str, float] = {}
+    units = vad_units(segmenter, streams, scene_s, scene_detector=scene_detector, timing=timing)
     if sync:
         sync()
     t1 = time.perf_counter()
-    return _finish(model, streams, units, decode, 0, 1, t0, t1, sync)
+    return _finish(model, streams, units, decode, 0, 1, t0, t1, sync, timing=timing)
 
 
-def _finish(model, streams, units, decode, rank, world, t0, t1, sync, all_units: Optional[List[Unit]] = None) -> StreamResult:
+def _finish(model, streams, units, decode, rank, world, t0, t1, sync, all_units: Optional[List[Unit]] = None,
+            timing: Optional[Dict[str, float]] = None) -> StreamResult:
     pool = all_units if all_units is not None else units
     keep = shard_units(len(pool), rank, world, weights=[u.speech_s for u in pool]) if world > 1 else range(len(pool))
     my_units = [pool[i] for i in keep]
@@ -141,8 +156,11 @@ def _finish(model, streams, units, decode, rank, world, t0, t1, sync, all_units:
         sync()
     t2 = time.perf_counter()
     audio_s = sum(len(s) for s in streams) / SR
-    return StreamResult(segs, my_units, {"vad": t1 - t0, "transcribe": t2 - t1, "total": t2 - t0},
+    timing = timing or {}
+    scenes_s = float(timing.get("scenes", 0.0))
+    return StreamResult(segs, my_units, {"scenes": scenes_s, "vad": t1 - t0 - scenes_s, "transcribe": t2 - t1, "total": t2 - t0},
                         {"streams": len(streams), "audio_s": audio_s, "units": len(my_units), "units_total": len(pool),
+                         "scenes": int(timing.get("n_scenes", 0)),
                          "unit_audio_s": sum((u.end_sample - u.start_sample) for u in my_units) / SR,
                          "speech_s": sum(u.speech_s for u in my_units)})
 
@@ -158,7 +176,7 @@ def units_from_tensor(t) -> List[Unit]:
 
 
 def transcribe_streams_distributed(model, segmenter, streams: Sequence[np.ndarray], decode: Optional[dict] = None, scene_s: float = 29.0,
-                                   sync=None, device="cuda") -> StreamResult:
+                                   sync=None, device="cuda", scene_detector=None) -> StreamResult:
     """Config-4 shape under torch.distributed: rank r gates the streams ``s % world == r``, the (tiny) unit lists are all-gathered,
     the units are dealt by speech seconds, every rank transcribes its share.  The caller gathers the segment records."""
     import torch
@@ -167,7 +185,8 @@ def transcribe_streams_distributed(model, segmenter, streams: Sequence[np.ndarra
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
     t0 = time.perf_counter()
     mine = [k for k in range(len(streams)) if k % world == rank]
-    units = vad_units(segmenter, [streams[k] for k in mine], scene_s, stream_ids=mine)
+    timing: Dict[str, float] = {}
+    units = vad_units(segmenter, [streams[k] for k in mine], scene_s, stream_ids=mine, scene_detector=scene_detector, timing=timing)
     if sync:
         sync()
     all_units = units
@@ -185,4 +204,4 @@ def transcribe_streams_distributed(model, segmenter, streams: Sequence[np.ndarra
         all_units = [u for r in range(world) for u in units_from_tensor(got[r][: int(counts[r])].cpu())]
         all_units.sort(key=lambda u: (u.stream, u.start_sample))
     t1 = time.perf_counter()
-    return _finish(model, streams, units, decode, rank, world, t0, t1, sync, all_units=all_units)
+    return _finish(model, streams, units, decode, rank, world, t0, t1, sync, all_units=all_units, timing=timing)

@@ -251,3 +251,50 @@ def speech_shaped_stream(seconds: float, seed: int, n_base: int = 40, clip_s: fl
         out[t: t + m] = c[:m]
         t += m
     return out
+
+
+def film_audio(seconds: float, seed: int, n_base: int = 40, clip_s: float = 30.0, sr: int = 16000) -> np.ndarray:
+    """A film-shaped stream for the scene detector (scene_detection_backends/auditok_backend.py: chapters separated by long
+    silences, oversized chapters holding shorter pauses): chapters of 2-80 s cut from seeded speech-shaped clips, separated by
+    0.4-4 s of room tone at about -75 dBFS (below the pass-1 gate of 32 dB re 1 LSB), pauses of 1.0-1.6 s at -68 dBFS inside the
+    long chapters (what pass 2 splits on), and now and then a 35-50 s "murmur" chapter at about 35 dB that passes the pass-1 gate
+    but not the pass-2 gate (the brute-force branch).  int16-quantised like every WAV hand-off of the reference."""
+    rng = np.random.default_rng(seed)
+    base = [speech_shaped_audio(clip_s, 200000 + 131 * seed + i, sr) for i in range(n_base)]
+    n = int(round(seconds * sr))
+    out = np.empty(n, dtype=np.float32)
+
+    def tone(m, dbfs):
+        return (rng.standard_normal(m) * 10 ** (dbfs / 20)).astype(np.float32)
+
+    t = 0
+    while t < n:
+        kind = rng.random()
+        if kind < 0.06:
+            m = int(rng.uniform(35.0, 50.0) * sr)
+            chunk = tone(m, -55.5)
+        else:
+            m = int(math.exp(rng.uniform(math.log(2.0), math.log(80.0))) * sr)
+            chunk = np.empty(m, dtype=np.float32)
+            u = 0
+            while u < m:
+                c = base[int(rng.integers(n_base))]
+                o = int(rng.integers(0, len(c) // 2))
+                k = min(len(c) - o, m - u)
+                chunk[u: u + k] = c[o: o + k]
+                u += k
+            u = int(rng.uniform(4.0, 18.0) * sr)
+            while u < m - sr:
+                k = min(int(rng.uniform(1.0, 1.6) * sr), m - sr - u)
+                chunk[u: u + k] = tone(k, -68.0)
+                u += k + int(rng.uniform(4.0, 24.0) * sr)
+        k = min(m, n - t)
+        out[t: t + k] = chunk[:k]
+        t += k
+        if t >= n:
+            break
+        g = min(int(math.exp(rng.uniform(math.log(0.4), math.log(4.0))) * sr), n - t)
+        out[t: t + g] = tone(g, -75.0)
+        t += g
+    q = np.round(np.clip(out, -1.0, 1.0) * 32767.0).astype(np.int16)
+    return (q.astype(np.float32) / 32768.0).astype(np.float32)
