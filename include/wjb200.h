@@ -201,11 +201,27 @@ int wjb_gemm_step_f16(const void* A, int64_t a_row_stride, int rows, int K, cons
 int wjb_gemm_step_ln_f16(const void* A, int64_t a_row_stride, int rows, int K, const void* ln_gamma, const void* ln_beta,
                          const void* W, int N, int ldw, const void* bias, const void* residual, void* out, int64_t out_row_stride,
                          int flags, int block_n, int cluster, int w_constant, void* stream);
+/* the decode step's form of it: no exchange.  ln_stats int64 [rows][2] = fixed-point (x 2^20) sum and sum of squares of every row of
+ * A, accumulated by the launches that produced A: a launch given out_stats (int64 [rows][2], zeroed by the caller) ADDS the same
+ * statistics of the fp16 values it stores, with 64-bit integer atomics (order-independent, bit-reproducible).  ln_stats NULL with
+ * gamma / beta set = the exchanging form above; out_stats NULL = none.  [whisper/model.py::ResidualAttentionBlock: attn_ln,
+ * cross_attn_ln, mlp_ln in front of the query / fc1 Linears, reached from whisper_pro_asr.py:433] */
+int wjb_gemm_step_stats_f16(const void* A, int64_t a_row_stride, int rows, int K, const void* ln_gamma, const void* ln_beta,
+                            const int64_t* ln_stats, const void* W, int N, int ldw, const void* bias, const void* residual, void* out,
+                            int64_t out_row_stride, int64_t* out_stats, int flags, int block_n, int cluster, int w_constant,
+                            void* stream);
 /* debugging aid: CTA 0 of every following GEMM launch writes a timeline (SM clock, global timer per pipeline event) into
  * `buf` (device, (32 + 512 * 32) uint64, zeroed by the caller; a ring of the last 512 launches); NULL switches it off. */
 void wjb_debug_gemm_trace(void* buf);
 /* debugging aid: launch the building blocks below with the programmatic-dependent-launch attribute, as the decode graph does */
 void wjb_debug_set_pdl(int on);
+/* debugging / measurement aid: placement options of the decode step (bit 0 LayerNorms folded into the step GEMMs through row
+ * statistics, bit 1 L2 prefetch of the next Linear's weights, bit 2 cross-attention K/V primed ahead of the dependency wait, bit 3
+ * evict-first K/V loads).  Results do not depend on bits 1-3; bit 0 moves rounding by < 1 fp16 ulp of a LayerNorm output in rare
+ * elements.  The library ships with bits 2 and 3 on (what measured fastest, profiles/r2_decode_flags.json); scripts/decode_flags_probe.py
+ * measures the combinations. */
+void wjb_debug_set_decode_flags(int flags);
+int wjb_debug_get_decode_flags(void);
 int wjb_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int n, void* stream);
 int wjb_attention_encoder_f16(const void* qkv, void* out, int batch, int T, int n_head, void* stream);
 /* single decoder step pieces */

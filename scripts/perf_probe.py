@@ -111,3 +111,31 @@ res["vad"] = {"ms": ms, "GBps_algorithmic": B * 1.92e6 / ms / 1e6, "windows": B 
 print(json.dumps(res, indent=1))
 Path("gpurun_out").mkdir(exist_ok=True)
 Path("gpurun_out/perf_probe.json").write_text(json.dumps(res, indent=1))
+
+# scene-split energy gate over a 2 h stream (exact integer sums per 50 ms block)
+from whisperjav_b200.scenes import B200SceneDetector  # noqa: E402
+stream = (torch.randn(16000 * 7200, device=DEV) * 0.05)
+det = B200SceneDetector()
+energy = det._energy_provider(stream)
+ms = timeit(lambda: energy([(0, stream.numel())], 800), iters=5)   # includes the 1.15 MB read-back of the sums
+res["scene_energy"] = {"ms_incl_readback": ms, "GBps_algorithmic": stream.numel() * 4 / ms / 1e6, "blocks": stream.numel() // 800}
+del stream
+
+# decode step with every row alive: large-v3, 64 windows, EOT suppressed so that no row ever ends (steady-state ms per step)
+from whisperjav_b200 import model as WM  # noqa: E402
+m = WM.load_model("large-v3", max_batch=B)
+xa = torch.randn(B, 1500, 1280, device=DEV, dtype=torch.float16) * 0.5
+tok = WM.Tokens(m.dims.n_vocab, "ja")
+for mode, kw in (("greedy", {}), ("beam2", {"beam_size": 2, "patience": 1.2})):
+    m.decode_features(xa, without_timestamps=True, suppress_tokens=f"-1,{tok.eot}", sample_len=24, **kw)   # warm-up / graph capture
+    torch.cuda.synchronize()
+    s0 = m.stats["decode_steps"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    m.decode_features(xa, without_timestamps=True, suppress_tokens=f"-1,{tok.eot}", sample_len=128, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    steps = m.stats["decode_steps"] - s0
+    res[f"decode_all_alive_{mode}"] = {"ms_per_step_incl_cross_kv_projection": e0.elapsed_time(e1) / steps, "steps": steps, "rows": B * (2 if kw else 1)}
+print(json.dumps({k: res[k] for k in res if k.startswith(("scene", "decode_all"))}, indent=1))
+Path("gpurun_out/perf_probe.json").write_text(json.dumps(res, indent=1))

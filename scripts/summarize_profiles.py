@@ -52,6 +52,17 @@ if len(idx) >= 2:
     md += ["", f"## one decode step ({len(step)} kernels, {sum(v for _, v in step):.1f} us)\n", "| kernel | launches | total us | avg us |", "|---|---|---|---|"]
     for k, v in sorted(a2.items(), key=lambda kv: -kv[1][1]):
         md.append(f"| `{k[:80]}` | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.2f} |")
+idx = [i for i, (n, _) in enumerate(seq) if "beam_select_kernel" in n]
+if len(idx) >= 2:
+    step = seq[idx[-2] + 1: idx[-1] + 1]
+    a2 = collections.defaultdict(lambda: [0, 0.0])
+    for n, v in step:
+        a2[n][0] += 1
+        a2[n][1] += v
+    md += ["", f"## one beam-search step, 64 windows x beam 2 ({len(step)} kernels, {sum(v for _, v in step):.1f} us)\n", "| kernel | launches | total us | avg us |",
+           "|---|---|---|---|"]
+    for k, v in sorted(a2.items(), key=lambda kv: -kv[1][1]):
+        md.append(f"| `{k[:80]}` | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.2f} |")
 (out / f"{tag}_launches.md").write_text("\n".join(md) + "\n")
 
 # ---- full captures

@@ -180,6 +180,64 @@ def test_gemm_step_fused_layernorm(lib, M, N, K, bn, S):
     assert torch.equal(A, a_before)  # the residual stream itself is not touched
 
 
+@pytest.mark.parametrize("M,N,K,bn,S", [(64, 1280, 1280, 0, 0), (64, 1280, 5120, 0, 0), (64, 1280, 1280, 64, 4), (128, 1280, 1280, 128, 8),
+                                        (96, 1280, 1280, 0, 0), (33, 384, 1536, 0, 0), (7, 384, 384, 64, 2)])
+def test_gemm_step_row_statistics_chain(lib, M, N, K, bn, S):
+    """The decode step's LayerNorm without a launch: a residual-producing step GEMM adds fixed-point row statistics of what it stores,
+    the next step GEMM normalises its activation tile from them.  (i) the statistics are the exact fixed-point sums of the stored
+    fp16 rows up to the rounding of the per-CTA fp32 partials, identical run to run; (ii) LayerNorm + Linear through them equals
+    LayerNorm -> fp16 -> Linear (torch fp32) like the exchanging kernel; (iii) a wrong statistic changes the result (it is used)."""
+    g = torch.Generator().manual_seed(M * 7 + N + K + bn + S)
+    A = (torch.randn(M, K, generator=g) * 0.7).half().to(DEV)
+    W = (torch.randn(N, K, generator=g) * (1.0 / K ** 0.5)).half().to(DEV)
+    bias = (torch.randn(N, generator=g) * 0.3).half().to(DEV)
+    res = (torch.randn(M, N, generator=g) * 2.0 + 0.4).half().to(DEV)
+    xs, sts = [], []
+    for rep in range(2):
+        x = res.clone()
+        st = torch.zeros(M, 2, dtype=torch.int64, device=DEV)
+        _lib.check(lib.wjb_gemm_step_stats_f16(_lib.ptr(A), K, M, K, None, None, None, _lib.ptr(W), N, K, _lib.ptr(bias), _lib.ptr(x), _lib.ptr(x), N,
+                                               _lib.ptr(st), 0, bn, S, 1, _lib.stream_ptr()), "producer")
+        torch.cuda.synchronize()
+        xs.append(x)
+        sts.append(st)
+    assert torch.equal(xs[0], xs[1]) and torch.equal(sts[0], sts[1])
+    ref_x = r16(r16(A.float() @ W.float().t() + bias.float()) + res.float())
+    assert (xs[0].float() - ref_x).abs().max().item() <= 8e-3 * max(1.0, ref_x.abs().max().item() / 4)
+    xd = xs[0].double()
+    want = torch.stack([xd.sum(1), (xd * xd).sum(1)], 1) * 2 ** 20
+    # sums of fp16 values: exact integers at the 2^20 scale, except that the few elements below 2^-10 round to the grid (<= 0.5 each)
+    assert (sts[0][:, 0].double() - want[:, 0]).abs().max().item() <= 4.0
+    err = (sts[0][:, 1].double() - want[:, 1]).abs().max().item()
+    assert err <= 0.5 * N, err                                          # every square rounded to the 2^-20 grid once, then exact adds
+    # consumer: N2 columns out of the normalised stream
+    K2, N2 = N, 3 * N if N <= 1280 else N
+    W2 = (torch.randn(N2, K2, generator=g) * 0.03).half().to(DEV)
+    b2 = (torch.randn(N2, generator=g) * 0.3).half().to(DEV)
+    gamma = (1.0 + 0.2 * torch.randn(K2, generator=g)).half().to(DEV)
+    beta = (0.1 * torch.randn(K2, generator=g)).half().to(DEV)
+    h = r16(torch.nn.functional.layer_norm(xs[0].float(), (K2,), gamma.float(), beta.float(), 1e-5))
+    ref = r16(h @ W2.float().t() + b2.float())
+    outs = []
+    for st in (sts[0], sts[0], sts[0] + torch.tensor([[1 << 27, 0]], device=DEV)):
+        out = torch.zeros(M, N2, dtype=torch.float16, device=DEV)
+        _lib.check(lib.wjb_gemm_step_stats_f16(_lib.ptr(xs[0]), K2, M, K2, _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(st), _lib.ptr(W2), N2, K2, _lib.ptr(b2),
+                                               None, _lib.ptr(out), N2, None, 0, 0, 0, 1, _lib.stream_ptr()), "consumer")
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    assert (outs[0].float() - ref).abs().max().item() <= 1.2e-2 * max(1.0, ref.abs().max().item() / 4)
+    assert not torch.equal(outs[0], outs[2])
+    # and it agrees with the stand-alone LayerNorm kernel + plain step GEMM to the last bit almost everywhere (same rounding points)
+    hk = torch.empty_like(xs[0])
+    _lib.check(lib.wjb_layernorm_f16(_lib.ptr(xs[0]), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(hk), M, K2, _lib.stream_ptr()), "ln")
+    out2 = torch.zeros(M, N2, dtype=torch.float16, device=DEV)
+    _lib.check(lib.wjb_gemm_step_f16(_lib.ptr(hk), K2, M, K2, _lib.ptr(W2), N2, K2, _lib.ptr(b2), None, _lib.ptr(out2), N2, 0, 0, 0, 1, _lib.stream_ptr()), "plain")
+    torch.cuda.synchronize()
+    assert (outs[0].float() - out2.float()).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item() / 4)
+    assert (outs[0] == out2).float().mean().item() >= 0.98
+
+
 @pytest.mark.parametrize("C_,stride,T_out", [(128, 1, 3000), (80, 1, 3000), (384, 2, 1500), (1280, 2, 1500)])
 def test_gemm_conv_im2col_free(lib, C_, stride, T_out):
     """k=3 convolution as a GEMM over overlapping rows of the channels-last padded input."""

@@ -242,3 +242,39 @@ def test_upstream_transcribe_keywords_are_accepted(tiny, clips):
     assert "segments" in out
     with pytest.raises(TypeError):
         m.transcribe(clips[2], language="ja", no_such_option=1)
+
+
+@pytest.mark.parametrize("mode", ["greedy", "beam", "words"])
+def test_two_tier_decoding_does_not_change_results(tiny, mode, monkeypatch):
+    """More windows than ``max_batch``: first-tier passes stop at a step cap, unfinished windows are pooled and decoded again
+    (StepCapPlanner).  Everything a caller sees -- tokens, segment times, word times, probabilities -- must equal the single-tier
+    run bit for bit, and the capped run must really have cut windows off."""
+    dims, w, m, pw = tiny
+    many = [speech_shaped_audio(4.0 + 1.7 * (i % 9), 7000 + i) for i in range(27)]
+    kw = dict(language="ja", temperature=0.0, condition_on_previous_text=False, max_initial_timestamp=0.0, no_speech_threshold=0.6,
+              logprob_threshold=-1.0, compression_ratio_threshold=2.4)
+    if mode == "beam":
+        kw.update(beam_size=2, patience=1.2)
+    if mode == "words":
+        kw.update(word_timestamps=True)
+    monkeypatch.setattr(M.WhisperB200, "tiered_decode", False)
+    plain = m.transcribe_batch(many, **kw)
+    steps_plain = m.stats["decode_steps"]
+    monkeypatch.setattr(M.WhisperB200, "tiered_decode", True)
+    monkeypatch.setattr(M.StepCapPlanner, "cap", lambda self: 12 if self.obs else None)   # force a low cap after the first pass
+    before = m.stats.get("windows_redecoded", 0)
+    tiered = m.transcribe_batch(many, **kw)
+    assert m.stats.get("windows_redecoded", 0) > before
+    assert [r["text"] for r in tiered] == [r["text"] for r in plain]
+    for a, b in zip(tiered, plain):
+        assert len(a["segments"]) == len(b["segments"])
+        for sa, sb in zip(a["segments"], b["segments"]):
+            assert sa["tokens"] == sb["tokens"] and sa["start"] == sb["start"] and sa["end"] == sb["end"] and sa["seek"] == sb["seek"]
+            assert sa["avg_logprob"] == sb["avg_logprob"] and sa["no_speech_prob"] == sb["no_speech_prob"]
+            if mode == "words":
+                assert [(x["word"], x["start"], x["end"]) for x in sa["words"]] == [(x["word"], x["start"], x["end"]) for x in sb["words"]]
+    monkeypatch.undo()
+    # and with the real planner the call still gives the same answer
+    auto = m.transcribe_batch(many, **kw)
+    assert [[s["tokens"] for s in r["segments"]] for r in auto] == [[s["tokens"] for s in r["segments"]] for r in plain]
+    assert steps_plain > 0

@@ -24,11 +24,18 @@ class _Scripted(M.WhisperB200):
     def _decode_with_prompts(self, xa, prompts, temperature, language, task, decode_options, seed=0):
         ids = [int(v) for v in xa[:, 0].tolist()]
         self.calls.append((temperature, ids, seed))
+        self.sample_lens = getattr(self, "sample_lens", []) + [decode_options.get("sample_len")]
         out = []
         for i in ids:
             k = self.draw.get((i, temperature), 0)
             self.draw[(i, temperature)] = k + 1
-            out.append(self.script[(i, temperature, k)])
+            r = self.script[(i, temperature, k)]
+            cap = decode_options.get("sample_len")
+            if cap is not None and len(r.tokens) >= cap:   # the device stops at the cap: no EOT yet
+                r = M.DecodingResult(tokens=r.tokens[:cap], text=r.text[:cap], avg_logprob=r.avg_logprob, no_speech_prob=r.no_speech_prob,
+                                     temperature=r.temperature, compression_ratio=r.compression_ratio, sum_logprob=r.sum_logprob,
+                                     complete=False, steps_needed=cap)
+            out.append(r)
         return out
 
 
@@ -87,3 +94,43 @@ def test_thresholds_can_be_disabled():
     m = _Scripted(script)
     out = m._decode_with_fallback(torch.zeros(1, 1), [[]], [0.0, 0.5], 1, "ja", "transcribe", {}, None, None, None)
     assert out[0].temperature == 0.0 and [c[0] for c in m.calls] == [0.0]
+
+
+def test_step_cap_keeps_cut_off_windows_out_of_the_ladder():
+    """A first-tier pass with a step cap (StepCapPlanner): windows that had not ended come back incomplete and are neither accepted
+    nor sent up the temperature ladder; the others behave exactly as without the cap; later temperatures run uncapped."""
+    temps = [0.0, 0.4]
+    script = {}
+    for t in temps:
+        script[(0, t, 0)] = _res([5, 6, 7], -0.3, 1.2, 0.1, t)                        # short and fine
+        script[(1, t, 0)] = _res(list(range(100, 140)), -0.3, 1.2, 0.1, t)            # 40 tokens: cut off by a cap of 16
+        script[(2, t, 0)] = _res([8, 9], -1.7, 1.1, 0.2, t) if t == 0.0 else _res(list(range(30)), -0.5, 1.1, 0.2, t)   # short, falls back
+    m = _Scripted(script)
+    xa = torch.arange(3, dtype=torch.float32).view(3, 1)
+    out = m._decode_with_fallback(xa, [[]] * 3, temps, 1, "ja", "transcribe", {}, 2.4, -1.0, 0.6, step_cap=16)
+    assert out[0].complete and out[0].tokens == [5, 6, 7]
+    assert not out[1].complete and len(out[1].tokens) == 16
+    assert out[2].complete and out[2].temperature == 0.4 and len(out[2].tokens) == 30   # the T = 0.4 pass was not capped
+    assert [c[:2] for c in m.calls] == [(0.0, [0, 1, 2]), (0.4, [2])] and m.sample_lens == [16, None]
+    # uncapped: the same windows, window 1 whole
+    m2 = _Scripted(script)
+    out2 = m2._decode_with_fallback(xa, [[]] * 3, temps, 1, "ja", "transcribe", {}, 2.4, -1.0, 0.6)
+    assert [o.tokens for o in out2] == [[5, 6, 7], list(range(100, 140)), list(range(30))] and out2[0].tokens == out[0].tokens
+
+
+def test_step_cap_planner_picks_the_cheapest_cap_and_stays_off_when_it_does_not_pay():
+    mk = lambda n, done=True: M.DecodingResult(tokens=[1] * n, complete=done, steps_needed=n)   # noqa: E731
+    p = M.StepCapPlanner(full=224, min_obs=32)
+    assert p.cap() is None                                  # nothing seen yet: first pass runs uncapped
+    p.observe([mk(20 + (k % 10)) for k in range(60)] + [mk(224) for _ in range(4)])   # 6 % stragglers at the limit
+    c = p.cap()
+    assert c == 32                                          # 32 + 224 * 4/64 = 46 steps per pass instead of 224
+    q = M.StepCapPlanner(full=224, min_obs=32)
+    q.observe([mk(200 + (k % 20)) for k in range(64)])      # everything long: capping buys nothing
+    assert q.cap() is None
+    r = M.StepCapPlanner(full=224, min_obs=32)
+    r.observe([mk(16, done=False) for _ in range(40)] + [mk(10) for _ in range(24)])  # censored windows count as full length
+    assert r.cap() is None or r.cap() >= 8
+    u = M.StepCapPlanner(full=224, min_obs=32)
+    u.observe([mk(30) for _ in range(64)])                  # uniform lengths: the pass already ends at 30
+    assert u.cap() is None

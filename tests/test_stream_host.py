@@ -123,3 +123,37 @@ def test_sharded_run_world2_gloo_matches_single():
     assert tot0 == tot1 == single.stats["units"] and n0 + n1 == tot0 and min(n0, n1) > 0
     assert abs(sp0 - sp1) <= 0.1 * (sp0 + sp1)                                          # dealt by speech seconds: balanced
     assert all0 == all1 == expect                                                       # every rank ends with every record
+
+
+class NumpySceneDetector:
+    """The product's two-pass driver (whisperjav_b200.scenes.two_pass) with the oracle's numpy twin of the energy kernel."""
+
+    def detect(self, audio, sample_rate=16000):
+        from oracle import scene_oracle as SO
+        from whisperjav_b200 import scenes as SC
+        return SC.two_pass(SC.SceneConfig(), len(audio), sample_rate, lambda regions, window: SO.window_sumsq(audio, regions, window))
+
+
+def test_stream_takes_its_scenes_from_the_detector():
+    """The silence detector's scenes replace the fixed 29 s cut: units never cross a detected scene, nothing of a silent gap is
+    transcribed, and the scenes are the ones the detector reports."""
+    a = np.zeros(int(200 * SR), np.float32)
+    rng = np.random.default_rng(4)
+    # three chapters (8 s, 65 s with 1.2 s pauses inside, 20 s) separated by > 1.8 s of digital silence
+    spans = [(5.0, 13.0), (17.0, 82.0), (90.0, 110.0)]
+    for s0, s1 in spans:
+        a[int(s0 * SR): int(s1 * SR)] = 0.9
+    for p0 in (30.0, 47.5, 66.0):
+        a[int(p0 * SR): int((p0 + 1.2) * SR)] = 0.0
+    det = NumpySceneDetector()
+    scenes, story, _ = det.detect(a, SR)
+    assert [(round(x, 2), round(y, 2)) for x, y in story] == [(5.0, 13.0), (17.0, 82.0), (90.0, 110.0)]
+    assert len(scenes) == 6 and all(s.end_sec - s.start_sec <= 29.0 for s in scenes)
+    m, seg = FakeModel(), FakeSegmenter()
+    r = S.transcribe_streams(m, seg, [a], decode=dict(S.BALANCED_DECODE), scene_detector=det)
+    assert r.stats["scenes"] == 6 and r.stages_s["scenes"] > 0
+    cuts = [(int(s.start_sec * SR), int(s.end_sec * SR)) for s in scenes]
+    for u in r.units:
+        assert any(c0 <= u.start_sample and u.end_sample <= c1 for c0, c1 in cuts)
+        assert np.all(np.abs(a[u.start_sample: u.end_sample][[1, -2]]) > 0.5)
+    assert sum(u.end_sample - u.start_sample for u in r.units) <= sum(c1 - c0 for c0, c1 in cuts)

@@ -223,6 +223,7 @@ struct wjb_model {
     float* align_prob = nullptr;
     const void *g_align_qk = nullptr, *g_align_len = nullptr, *g_align_prob = nullptr;
     int g_align_steps = 0;
+    int g_flags = -1;
     void* enc_tap = nullptr;  // test hook (wjb_encoder_set_tap): residual stream after block index k * enc_tap_every - 1
     int enc_tap_every = 0;
     const __half* h16(const std::string& name) const { return reinterpret_cast<const __half*>(blob + L.off(name)); }
@@ -499,6 +500,7 @@ struct DecWs {
     __half *x, *h, *qkv, *q, *a, *mlp, *logits, *self_kv;
     DecodeCtl* ctl;
     unsigned char* done;
+    long long* lnstat;  // [3 * n_text_layer + 1 LayerNorm sites][B][2] fixed-point row statistics of the residual stream (gemm_step.cu)
     int logits_stride;
     size_t total;
 };
@@ -522,6 +524,7 @@ static DecWs dec_ws(const wjb_dims& d, int B, uint8_t* base) {
     w.self_kv = (__half*)take((size_t)d.n_text_layer * B * 2 * d.n_text_head * d.n_text_ctx * 64 * 2);
     w.ctl = (DecodeCtl*)take(sizeof(DecodeCtl));
     w.done = (unsigned char*)take((size_t)B);
+    w.lnstat = (long long*)take((size_t)(3 * d.n_text_layer + 1) * B * 2 * sizeof(long long));
     w.total = off;
     return w;
 }
@@ -670,22 +673,35 @@ int wjb_align_prefill(wjb_model* m, const void* cross_kv, const int32_t* tokens,
     return 0;
 }
 
+// Decode-step placement options (wjb_debug_set_decode_flags; measured with scripts/decode_flags_probe.py, profiles/r2_decode_flags.json):
+//   1  LayerNorms folded into the consuming step GEMM through the producers' row statistics (gemm_step.cu)   -- no gain: off
+//   2  every step GEMM pulls the NEXT Linear's weights into L2 while it runs (cp.async.bulk.prefetch.L2)     -- +2 %: off
+//   4  the cross-attention primes its K/V ring before the programmatic-dependent-launch wait                 -- on
+//   8  K/V bulk copies carry an L2 evict-first policy (the stream must not push the layer's weights out of L2) -- -1 %: on
+static int g_decode_flags = 4 | 8;
+
 // The kernels of one decoder step for B rows on stream s (captured into the step graph).
 static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B, const wjb_decode_opts& o, const uint8_t* suppress_mask,
                        int32_t* tokens, float* slp, float* nsp, int32_t* out_len, cudaStream_t s, const BeamBufs* beam = nullptr) {
     const wjb_dims& d = m->d;
     const int n = d.n_text_state, H = d.n_text_head, T = d.n_audio_ctx;
     // LayerNorm (ln_g / ln_b, may be null) into w.h, then the Linear
+    const int chunk = B <= 128 ? B : (B + 1) / 2 <= 128 ? (B + 1) / 2 : 128;
+    auto step_ok = [&](int N, int K) { return gemm_step_supported(chunk, N, K) && gemm_step_supported(B - (B - 1) / chunk * chunk, N, K); };
+    // site_in: LayerNorm site whose statistics the producers of A accumulated (-1: run the LayerNorm as its own launch);
+    // site_out: site this Linear's output rows are the input of (their statistics are added by its epilogue; -1: none)
     auto linear = [&](const __half* A, int K, const __half* W, int ldw, const __half* bias, const __half* res, __half* out, int N,
-                      long long out_stride, int flags, const __half* ln_g = nullptr, const __half* ln_b = nullptr) {
-        if (ln_g) {
+                      long long out_stride, int flags, const __half* ln_g = nullptr, const __half* ln_b = nullptr, int site_in = -1,
+                      int site_out = -1, const __half* next_w = nullptr, size_t next_w_bytes = 0) {
+        const bool step_kernel = step_ok(N, K);
+        const bool fold_ln = ln_g && site_in >= 0 && step_kernel;
+        if (ln_g && !fold_ln) {
             if (int e = launch_layernorm(A, ln_g, ln_b, w.h, B, K, s)) return e;
             A = w.h;
         }
         // the cluster split-K kernel written for exactly this shape class (gemm_step.cu) takes <= 128 rows: larger row counts
         // (64 windows x beam 3 = 192) go through it in row chunks -- the weights stream twice, still well ahead of the general kernel
-        const int chunk = B <= 128 ? B : (B + 1) / 2 <= 128 ? (B + 1) / 2 : 128;
-        if (gemm_step_supported(chunk, N, K) && gemm_step_supported(B - (B - 1) / chunk * chunk, N, K)) {
+        if (step_kernel) {
             for (int r0 = 0; r0 < B; r0 += chunk) {
                 const int rows = B - r0 < chunk ? B - r0 : chunk;
                 StepGemmArgs g;
@@ -702,6 +718,16 @@ static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B
                 g.out_row_stride = out_stride;
                 g.flags = flags;
                 g.w_constant = true;
+                if (fold_ln) {
+                    g.ln_gamma = ln_g;
+                    g.ln_beta = ln_b;
+                    g.ln_stats = w.lnstat + ((long long)site_in * B + r0) * 2;
+                }
+                if (site_out >= 0) g.out_stats = w.lnstat + ((long long)site_out * B + r0) * 2;
+                if ((g_decode_flags & 2) && next_w && r0 == 0) {
+                    g.prefetch = next_w;
+                    g.prefetch_bytes = next_w_bytes;
+                }
                 if (int e = launch_gemm_step(g, s)) return e;
             }
             return 0;
@@ -726,18 +752,28 @@ static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B
     // beam search: rows = windows x beams; token rows and the cache ancestry are double buffered by step parity, the rows of a
     // window share its cross K/V
     const int kv_div = beam ? beam->beam : 1;
+    // the residual stream's row statistics: site 3 i + {0, 1, 2} = input of layer i's attn_ln / cross_attn_ln / mlp_ln.  The embedding
+    // kernel writes site 0 and zeroes the others, every Linear that stores the stream adds to the site that reads it next.
+    const bool stats_ok = (g_decode_flags & 1) && step_ok(n, n) && step_ok(n, 4 * n);  // every producer of the stream (out, cross-out, fc2) must be a step GEMM
+    const int n_sites = stats_ok ? 3 * d.n_text_layer + 1 : 0;
     if (int e = launch_embed(beam ? beam->tokens : tokens, o.tokens_stride, m->h16("dec.emb"), m->h16("dec.pos"), w.x, w.ctl, B, n, s,
-                             beam ? beam->tokens_parity_stride : 0))
+                             beam ? beam->tokens_parity_stride : 0, w.lnstat, n_sites))
         return e;
+    auto site = [&](int k) { return stats_ok ? k : -1; };
     const size_t self_per_layer = (size_t)B * 2 * H * d.n_text_ctx * 64;
     const size_t cross_per_layer = (size_t)(B / kv_div) * 2 * H * T * 64;
     for (int i = 0; i < d.n_text_layer; ++i) {
         const std::string p = "dec." + std::to_string(i) + ".";
-        if (int e = linear(w.x, n, m->h16(p + "qkv.w"), n, m->h16(p + "qkv.b"), nullptr, w.qkv, 3 * n, 3 * n, 0, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"))) return e;
+        const size_t nn = (size_t)n * n * 2;  // bytes of an n x n fp16 weight
+        const std::string pn = "dec." + std::to_string(i + 1 < d.n_text_layer ? i + 1 : 0) + ".";  // the next step starts at layer 0 again
+        if (int e = linear(w.x, n, m->h16(p + "qkv.w"), n, m->h16(p + "qkv.b"), nullptr, w.qkv, 3 * n, 3 * n, 0, m->h16(p + "ln1.g"), m->h16(p + "ln1.b"), site(3 * i),
+                           -1, m->h16(p + "out.w"), nn))
+            return e;
         if (int e = launch_attn_dec_self(w.qkv, w.self_kv + i * self_per_layer, w.a, &w.ctl->step, w.done, B, H, d.n_text_ctx, s,
                                          beam ? beam->anc : nullptr, beam ? beam->anc_parity_stride : 0)) return e;
-        if (int e = linear(w.a, n, m->h16(p + "out.w"), n, m->h16(p + "out.b"), w.x, w.x, n, n, 0)) return e;
-        if (int e = linear(w.x, n, m->h16(p + "cq.w"), n, m->h16(p + "cq.b"), nullptr, w.q, n, n, 0, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"))) return e;
+        if (int e = linear(w.a, n, m->h16(p + "out.w"), n, m->h16(p + "out.b"), w.x, w.x, n, n, 0, nullptr, nullptr, -1, site(3 * i + 1), m->h16(p + "cq.w"), nn))
+            return e;
+        if (int e = linear(w.x, n, m->h16(p + "cq.w"), n, m->h16(p + "cq.b"), nullptr, w.q, n, n, 0, m->h16(p + "ln2.g"), m->h16(p + "ln2.b"), site(3 * i + 1))) return e;
         CrossCapture cap;
         const int sel0 = d.n_text_layer / 2;  // alignment heads: every head of the upper half of the layers (upstream default)
         if (m->align_qk && !beam && i >= sel0) {
@@ -746,12 +782,25 @@ static int decode_step(wjb_model* m, const DecWs& w, const void* cross_kv, int B
             cap.head_stride = (long long)m->align_steps * T;
             cap.step = &w.ctl->step;
         }
+        CrossTuning tune;
+        tune.early_kv = (g_decode_flags & 4) ? 1 : 0;
+        tune.evict_first = (g_decode_flags & 8) ? 1 : 0;
+        if (g_decode_flags & 2) {
+            tune.pf_ptr = m->h16(p + "cout.w");
+            tune.pf_bytes = nn;
+        }
         if (int e = launch_attn_dec_cross(w.q, reinterpret_cast<const __half*>(cross_kv) + i * cross_per_layer, w.a, w.done, B, H, T, s, kv_div,
-                                          cap.base ? &cap : nullptr))
+                                          cap.base ? &cap : nullptr, &tune))
             return e;
-        if (int e = linear(w.a, n, m->h16(p + "cout.w"), n, m->h16(p + "cout.b"), w.x, w.x, n, n, 0)) return e;
-        if (int e = linear(w.x, n, m->h16(p + "fc1.w"), n, m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, 4 * n, GEMM_GELU, m->h16(p + "ln3.g"), m->h16(p + "ln3.b"))) return e;
-        if (int e = linear(w.mlp, 4 * n, m->h16(p + "fc2.w"), 4 * n, m->h16(p + "fc2.b"), w.x, w.x, n, n, 0)) return e;
+        if (int e = linear(w.a, n, m->h16(p + "cout.w"), n, m->h16(p + "cout.b"), w.x, w.x, n, n, 0, nullptr, nullptr, -1, site(3 * i + 2), m->h16(p + "fc1.w"), 4 * nn))
+            return e;
+        if (int e = linear(w.x, n, m->h16(p + "fc1.w"), n, m->h16(p + "fc1.b"), nullptr, w.mlp, 4 * n, 4 * n, GEMM_GELU, m->h16(p + "ln3.g"), m->h16(p + "ln3.b"), site(3 * i + 2),
+                           -1, m->h16(p + "fc2.w"), 4 * nn))
+            return e;
+        // the last layer's output goes through ln (dec.ln) in front of the logits GEMM, which is not a step GEMM: no statistics needed
+        if (int e = linear(w.mlp, 4 * n, m->h16(p + "fc2.w"), 4 * n, m->h16(p + "fc2.b"), w.x, w.x, n, n, 0, nullptr, nullptr, -1,
+                           i + 1 < d.n_text_layer ? site(3 * i + 3) : -1, m->h16(pn + "qkv.w"), 3 * nn))
+            return e;
     }
     if (int e = linear(w.x, n, m->h16("dec.emb"), n, nullptr, nullptr, w.logits, d.n_vocab, w.logits_stride, 0, m->h16("dec.ln.g"), m->h16("dec.ln.b"))) return e;
     DecodeParams p;
@@ -827,7 +876,7 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
                      m->g_tokens == tokens && m->g_slp == sum_logprob && m->g_nsp == no_speech_prob && m->g_len == out_len &&
                      m->g_trace_logits == m->trace_logits && m->g_trace_sampled == m->trace_sampled && m->g_trace_forced == m->trace_forced &&
                      m->g_align_qk == m->align_qk && m->g_align_len == m->align_len && m->g_align_prob == m->align_prob &&
-                     m->g_align_steps == m->align_steps &&
+                     m->g_align_steps == m->align_steps && m->g_flags == g_decode_flags &&
                      memcmp(&m->g_opts, &okey, sizeof(okey)) == 0;
     if (!hit) {
         if (m->graph) {
@@ -866,6 +915,7 @@ int wjb_decode_greedy(wjb_model* m, const void* cross_kv, int batch, const wjb_d
         m->g_align_len = m->align_len;
         m->g_align_prob = m->align_prob;
         m->g_align_steps = m->align_steps;
+        m->g_flags = g_decode_flags;
     }
     const int check_every = o.check_every > 0 ? o.check_every : 8;
     int step = 0;
@@ -1041,8 +1091,17 @@ void wjb_debug_gemm_trace(void* buf) {
 int wjb_gemm_step_ln_f16(const void* A, int64_t a_row_stride, int rows, int K, const void* ln_gamma, const void* ln_beta, const void* W, int N,
                          int ldw, const void* bias, const void* residual, void* out, int64_t out_row_stride, int flags, int block_n,
                          int cluster, int w_constant, void* stream) {
+    return wjb_gemm_step_stats_f16(A, a_row_stride, rows, K, ln_gamma, ln_beta, nullptr, W, N, ldw, bias, residual, out, out_row_stride, nullptr, flags,
+                                   block_n, cluster, w_constant, stream);
+}
+
+int wjb_gemm_step_stats_f16(const void* A, int64_t a_row_stride, int rows, int K, const void* ln_gamma, const void* ln_beta, const int64_t* ln_stats,
+                            const void* W, int N, int ldw, const void* bias, const void* residual, void* out, int64_t out_row_stride,
+                            int64_t* out_stats, int flags, int block_n, int cluster, int w_constant, void* stream) {
     if (int e = ensure_init()) return e;
     StepGemmArgs g;
+    g.ln_stats = reinterpret_cast<const long long*>(ln_stats);
+    g.out_stats = reinterpret_cast<long long*>(out_stats);
     g.A = (const __half*)A;
     g.a_row_stride = a_row_stride;
     g.rows = rows;
@@ -1070,6 +1129,8 @@ int wjb_gemm_step_f16(const void* A, int64_t a_row_stride, int rows, int K, cons
                                 w_constant, stream);
 }
 void wjb_debug_set_pdl(int on) { set_pdl(on != 0); }
+void wjb_debug_set_decode_flags(int flags) { g_decode_flags = flags; }
+int wjb_debug_get_decode_flags(void) { return g_decode_flags; }
 
 int wjb_gemm_f16_splitk(const void* A, int64_t a_row_stride, int rows, int K, const void* W, int N, int ldw, const void* bias,
                         const void* residual, void* out, int64_t out_row_stride, int flags, int block_n, int splits, void* workspace,

@@ -437,9 +437,14 @@ template <int NQ>
 __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
                                                                              __half* __restrict__ out,
                                                                              const unsigned char* __restrict__ done, int H, int T, int kv_div,
-                                                                             const CrossCapture cap) {
-    pdl_prologue();
+                                                                             const CrossCapture cap, const CrossTuning tune) {
+    // K/V are constants of the decode run and `done` was written a whole step ago: only q depends on the previous kernel.  With
+    // tune.early_kv the ring is primed BEFORE the programmatic-dependent-launch wait, so the stream is in flight while the query
+    // projection in front of this kernel drains.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!tune.early_kv) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int h = blockIdx.x, b = blockIdx.y;
+    if (threadIdx.x == 0) l2_prefetch_share(tune.pf_ptr, tune.pf_bytes, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y);
     const int row0 = b * NQ;  // first query row of this CTA
     if (done && done[row0]) return;  // the beams of a window finish together
     extern __shared__ __align__(128) uint8_t cb_smem[];
@@ -455,16 +460,24 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
     const uint8_t* Vg = reinterpret_cast<const uint8_t*>(kv + ((long long)(bk * 2 * H + H + h) * T) * 64);
     const int nck = (T + kCbKeys - 1) / kCbKeys;  // chunks per matrix
     const int total = 2 * nck;
+    const unsigned long long kv_policy = tune.evict_first ? l2_policy_evict_first() : 0ull;
     auto chunk_src = [&](int c) { return (c < nck ? Kg : Vg) + (size_t)(c % nck) * kCbStageBytes; };
     auto chunk_keys = [&](int c) { return min(kCbKeys, T - (c % nck) * kCbKeys); };
     auto issue = [&](int c) {
         const int st = c % kCbStages;
         const uint32_t bytes = chunk_keys(c) * 128;
         mbar_arrive_expect_tx(&full[st], bytes);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(ring + st * kCbStageBytes)),
-                     "l"(chunk_src(c)), "r"(bytes), "r"(smem_u32(&full[st]))
-                     : "memory");
+        if (tune.evict_first) {  // the K/V stream is read once per step: do not let it push the layer's weights out of L2
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                             smem_u32(ring + st * kCbStageBytes)),
+                         "l"(chunk_src(c)), "r"(bytes), "r"(smem_u32(&full[st])), "l"(kv_policy)
+                         : "memory");
+        } else {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(ring + st * kCbStageBytes)),
+                         "l"(chunk_src(c)), "r"(bytes), "r"(smem_u32(&full[st]))
+                         : "memory");
+        }
     };
     if (tid == 0) {
         for (int i = 0; i < kCbStages; ++i) mbar_init(&full[i], 1);
@@ -473,6 +486,7 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
     __syncthreads();
     if (tid == 0)
         for (int c = 0; c < kCbStages && c < total; ++c) issue(c);
+    if (tune.early_kv) asm volatile("griddepcontrol.wait;" ::: "memory");  // q (and `out`) belong to the chain
 
     const int chunk16 = tid & 7, slot = tid >> 3;  // 16 key slots x 8 sixteen-byte pieces
     float qf[NQ][8];
@@ -599,9 +613,10 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
 
 template <int NQ>
 static int launch_cross_bulk(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T, int kv_div,
-                             cudaStream_t s, const CrossCapture& cap) {
+                             cudaStream_t s, const CrossCapture& cap, const CrossTuning& tune) {
     dim3 grid(H, B / NQ);
-    cudaError_t e = launch_k(attn_dec_cross_bulk_kernel<NQ>, grid, dim3(kCrossThreads), (size_t)cb_smem_bytes(NQ), s, q, kv, out, done, H, T, kv_div, cap);
+    cudaError_t e = launch_k(attn_dec_cross_bulk_kernel<NQ>, grid, dim3(kCrossThreads), (size_t)cb_smem_bytes(NQ), s, q, kv, out, done, H, T, kv_div, cap,
+                             tune);
     if (e != cudaSuccess) return set_error("attn_dec_cross_bulk launch: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -618,20 +633,21 @@ int attn_cross_init() {
 }
 
 int launch_attn_dec_cross(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T,
-                          cudaStream_t s, int kv_div, const CrossCapture* capture) {
+                          cudaStream_t s, int kv_div, const CrossCapture* capture, const CrossTuning* tuning) {
     const CrossCapture cap = capture ? *capture : CrossCapture{};
+    const CrossTuning tune = tuning ? *tuning : CrossTuning{};
     if (cap.base && kv_div != 1) return set_error("attn_dec_cross: score capture needs one query per window");
     if (kv_div < 1) kv_div = 1;
     if (T > kCrossMaxT) return set_error("attn_dec_cross: T %d > %d", T, kCrossMaxT);
     // beam search: the beams of a window share one pass over its K/V when they fit one CTA
     if (kv_div > 1 && kv_div <= kCbMaxQ && B % kv_div == 0) {
         switch (kv_div) {
-            case 2: return launch_cross_bulk<2>(q, kv, out, done, B, H, T, kv_div, s, cap);
-            case 3: return launch_cross_bulk<3>(q, kv, out, done, B, H, T, kv_div, s, cap);
-            case 4: return launch_cross_bulk<4>(q, kv, out, done, B, H, T, kv_div, s, cap);
+            case 2: return launch_cross_bulk<2>(q, kv, out, done, B, H, T, kv_div, s, cap, tune);
+            case 3: return launch_cross_bulk<3>(q, kv, out, done, B, H, T, kv_div, s, cap, tune);
+            case 4: return launch_cross_bulk<4>(q, kv, out, done, B, H, T, kv_div, s, cap, tune);
         }
     }
-    return launch_cross_bulk<1>(q, kv, out, done, B, H, T, kv_div, s, cap);
+    return launch_cross_bulk<1>(q, kv, out, done, B, H, T, kv_div, s, cap, tune);
 }
 
 }  // namespace wjb

@@ -202,6 +202,27 @@ WJB_DEVINL void pdl_prologue() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// A share of a constant region (the next Linear's weights) pulled into L2 ahead of its use: CTA `cta` of `n_cta` prefetches
+// bytes [cta * per, (cta + 1) * per) with cp.async.bulk.prefetch.L2 (no destination, no completion to wait for).
+WJB_DEVINL void l2_prefetch_share(const void* base, unsigned long long bytes, unsigned cta, unsigned n_cta) {
+    if (!base || bytes == 0) return;
+    const unsigned long long per = ((bytes + n_cta - 1) / n_cta + 127ull) & ~127ull;
+    const unsigned long long off = per * cta;
+    if (off >= bytes) return;
+    unsigned long long n = bytes - off < per ? bytes - off : per;
+    n &= ~15ull;
+    const char* ptr = reinterpret_cast<const char*>(base) + off;
+    for (unsigned long long o = 0; o < n; o += 16384ull) {
+        const unsigned sz = (unsigned)(n - o < 16384ull ? n - o : 16384ull);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + o), "r"(sz) : "memory");
+    }
+}
+WJB_DEVINL unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 // ------------------------------------------------------------------ math
 WJB_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // Exact-erf GELU through the Abramowitz-Stegun 7.1.26 rational form of erf (|error| <= 1.5e-7, far below the

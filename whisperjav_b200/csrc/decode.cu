@@ -11,24 +11,53 @@
 namespace wjb {
 
 // parity_stride != 0: beam search keeps two token buffers `parity_stride` ints apart; position `step` is read from buffer step & 1
+// lnstat (n_sites > 0): [n_sites][B][2] fixed-point (x 2^20) sum / sum of squares of the residual-stream rows at every LayerNorm
+// site of the step (gemm_step.cu): this kernel stores its row's statistics at site 0 and zeroes the row's accumulators of the others
 __global__ void embed_kernel(const int* __restrict__ tokens, int tokens_stride, long long parity_stride, const __half* __restrict__ emb,
-                             const __half* __restrict__ pos, __half* __restrict__ x, const DecodeCtl* __restrict__ ctl, int n) {
+                             const __half* __restrict__ pos, __half* __restrict__ x, const DecodeCtl* __restrict__ ctl, int n,
+                             long long* __restrict__ lnstat, int n_sites) {
     pdl_prologue();
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, B = gridDim.x;
     const int step = ctl->step;
     const int tok = tokens[(step & 1) * parity_stride + (long long)b * tokens_stride + step];
     const __half2* e = reinterpret_cast<const __half2*>(emb + (long long)tok * n);
     const __half2* p = reinterpret_cast<const __half2*>(pos + (long long)step * n);
     __half2* o = reinterpret_cast<__half2*>(x + (long long)b * n);
+    long long sfx = 0, qfx = 0;
     for (int i = threadIdx.x; i < n / 2; i += blockDim.x) {
         const float2 a = __half22float2(e[i]), c = __half22float2(p[i]);
-        o[i] = __floats2half2_rn(a.x + c.x, a.y + c.y);
+        const __half2 v = __floats2half2_rn(a.x + c.x, a.y + c.y);
+        o[i] = v;
+        const float2 f = __half22float2(v);
+        sfx += __float2ll_rn(f.x * 1048576.0f) + __float2ll_rn(f.y * 1048576.0f);   // exact (see gemm_step.cu)
+        qfx += __float2ll_rn(f.x * f.x * 1048576.0f) + __float2ll_rn(f.y * f.y * 1048576.0f);
+    }
+    if (n_sites > 0) {
+        __shared__ long long red[2][4];
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            sfx += __shfl_xor_sync(0xffffffffu, sfx, o2);
+            qfx += __shfl_xor_sync(0xffffffffu, qfx, o2);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            red[0][threadIdx.x >> 5] = sfx;
+            red[1][threadIdx.x >> 5] = qfx;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            lnstat[2 * b] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+            lnstat[2 * b + 1] = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+        }
+        for (int k = 1 + threadIdx.x; k < n_sites; k += blockDim.x) {
+            lnstat[((long long)k * B + b) * 2] = 0;
+            lnstat[((long long)k * B + b) * 2 + 1] = 0;
+        }
     }
 }
 
 int launch_embed(const int* tokens, int tokens_stride, const __half* emb, const __half* pos, __half* x, const DecodeCtl* ctl, int B,
-                 int n, cudaStream_t s, long long parity_stride) {
-    launch_k(embed_kernel, dim3(B), dim3(128), 0, s, tokens, tokens_stride, parity_stride, emb, pos, x, ctl, n);
+                 int n, cudaStream_t s, long long parity_stride, long long* lnstat, int n_sites) {
+    launch_k(embed_kernel, dim3(B), dim3(128), 0, s, tokens, tokens_stride, parity_stride, emb, pos, x, ctl, n, lnstat, n_sites);
     WJB_CHECK_LAUNCH("embed");
     return 0;
 }

@@ -20,6 +20,11 @@
 //     runs inside: every CTA holds a K slice of all rows, so the cluster adds per-row partial sums through distributed
 //     shared memory (two passes: mean, then sum of squared deviations, fp32, rank order), normalises its tile in place
 //     and hands it to the MMA thread -- one launch and one global round trip less per LayerNorm,
+//   * ... or, in the decode step, without any exchange: the GEMM that PRODUCES the residual stream (out / cross-out / fc2) adds
+//     per-row sum and sum of squares of the fp16 values it stores to a fixed-point accumulator (64-bit integer atomics: the
+//     order of the adds cannot change the result), and the GEMM behind the LayerNorm reads two integers per row, normalises
+//     its tile in shared memory with the reference's rounding points (fp32 statistics of the fp16 row, fp16-rounded output)
+//     and starts its MMAs: 97 LayerNorm launches per decoder step become 1,
 //   * weights are constants, so their TMA loads are issued BEFORE griddepcontrol.wait: under programmatic dependent
 //     launch the CTAs of this GEMM are resident while the previous kernels of the step still run and the weight
 //     slices are already in shared memory when the activations become valid.
@@ -47,6 +52,10 @@ struct StepDev {
     int w_early;      // 1 = weights may be fetched before the previous kernel has finished
     const __half* ln_g;  // LayerNorm over the K columns of every activation row, applied to the tile in shared memory before the
     const __half* ln_b;  // MMAs (null = activations are used as they are)
+    const long long* ln_stats;  // [rows][2] fixed-point (2^20) sum / sum of squares of every activation row: no cluster exchange needed
+    long long* out_stats;       // [rows][2] accumulators this GEMM adds the statistics of its OUTPUT rows to (null = none)
+    const void* pf_ptr;         // constant region (the next Linear's weights) this grid pulls into L2 while it runs (null = none)
+    unsigned long long pf_bytes;
     unsigned long long* trace;
 };
 
@@ -102,6 +111,7 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
     float* lnbuf = reinterpret_cast<float*>(bars + 2 * kStepMaxStages + 8);  // [2 passes][S][128 rows] partial sums
     const bool ln = p.ln_g != nullptr;
+    const bool ln_x = ln && p.ln_stats == nullptr;  // LayerNorm with the statistics exchanged inside the cluster
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -142,6 +152,7 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_arrive_expect_tx(&w_full[i], kBBytes);
             tma_load_2d(w_tiles + i * kBBytes, &tmB, &w_full[i], (kb0 + i) * kStepBlockK, nt * BN);
         }
+        l2_prefetch_share(p.pf_ptr, p.pf_bytes, blockIdx.x, gridDim.x);
         WJB_STEP_TRACE(1);
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -149,7 +160,7 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     cluster_arrive();  // "this CTA is running": matched by the wait in front of the first remote store
-    if (ln) cluster_wait();  // ... which in the LayerNorm variant is the exchange of partial sums, so wait right away
+    if (ln_x) cluster_wait();  // ... which in the exchanging LayerNorm variant is the exchange of partial sums, so wait right away
     const uint32_t tmem_base = *tmem_slot;
     if (lane == 0) trace_row = trace_sh;
 
@@ -166,7 +177,7 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             WJB_STEP_TRACE(3);
         }
         __syncwarp();
-        if (ln) {  // every thread of the cluster takes part in the two partial-sum exchanges
+        if (ln_x) {  // every thread of the cluster takes part in the two partial-sum exchanges
             cluster_arrive();
             cluster_wait();
             cluster_arrive();
@@ -188,7 +199,7 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (ln) {
+        if (ln_x) {
             cluster_arrive();
             cluster_wait();
             cluster_arrive();
@@ -253,8 +264,63 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp >= 2) {
         const int q = warp & 3;  // TMEM lane quadrant
         const int row = q * 32 + lane;
+        if (ln && !ln_x) {  // gamma / beta of this CTA's K slice are constants: stage them in shared memory ahead of the dependency wait
+            const int t = threadIdx.x - 64;
+            uint4* gsm = reinterpret_cast<uint4*>(lnbuf + 512);  // [nkb * 8] gamma, then [nkb * 8] beta (16-byte pieces of 8 halfs)
+            const uint4* gg = reinterpret_cast<const uint4*>(p.ln_g + (long long)kb0 * kStepBlockK);
+            const uint4* gb = reinterpret_cast<const uint4*>(p.ln_b + (long long)kb0 * kStepBlockK);
+            for (int idx = t; idx < nkb * 8; idx += 128) {
+                gsm[idx] = __ldg(gg + idx);
+                gsm[nkb * 8 + idx] = __ldg(gb + idx);
+            }
+        }
         asm volatile("griddepcontrol.wait;" ::: "memory");  // the epilogue reads the residual and overwrites `out`
-        if (ln) {
+        if (ln && !ln_x) {
+            // ===================== LayerNorm from the producer's row statistics, tile normalised in place =====================
+            const int t = threadIdx.x - 64;
+            float2* rowstat = reinterpret_cast<float2*>(lnbuf);  // [rows] (mean, rstd)
+            const uint4* gsm = reinterpret_cast<const uint4*>(lnbuf + 512);
+            if (t < p.rows) {
+                const long long sfx = p.ln_stats[2 * t], qfx = p.ln_stats[2 * t + 1];
+                const double inv = 1.0 / ((double)p.K * 1048576.0);
+                const double mean = (double)sfx * inv;
+                double var = (double)qfx * inv - mean * mean;
+                var = var > 0.0 ? var : 0.0;
+                rowstat[t] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait_warp(&a_full[0], 0);
+            if (p.a_chunks > 1) mbar_wait_warp(&a_full[1], 0);
+            // thread -> 16-byte chunk c of every k block, rows (t >> 3) + 16 j: gamma / beta are loaded once per k block
+            const int c = t & 7, r0 = t >> 3;
+            for (int i = 0; i < nkb; ++i) {
+                const uint4 g = gsm[i * 8 + c];
+                const uint4 bb = gsm[nkb * 8 + i * 8 + c];
+                const __half2* gh = reinterpret_cast<const __half2*>(&g);
+                const __half2* bh = reinterpret_cast<const __half2*>(&bb);
+                float2 gf[4], bf[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    gf[e] = __half22float2(gh[e]);
+                    bf[e] = __half22float2(bh[e]);
+                }
+                for (int lrow = r0; lrow < p.rows; lrow += 16) {
+                    const float2 st = rowstat[lrow];
+                    uint4* px = reinterpret_cast<uint4*>(a_tiles + i * p.a_tile + lrow * 128 + ((c ^ (lrow & 7)) << 4));
+                    uint4 u = *px;
+                    __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __half22float2(h2[e]);
+                        h2[e] = __floats2half2_rn((f.x - st.x) * st.y * gf[e].x + bf[e].x, (f.y - st.x) * st.y * gf[e].y + bf[e].y);
+                    }
+                    *px = u;
+                }
+            }
+            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's reads of shared memory
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+        } else if (ln) {
             // ===================== LayerNorm of the activation tile, in place =====================
             // rows <= 64: two threads per row (4 of the 8 16-byte chunks of a k block each), else one thread per row
             const int t = threadIdx.x - 64;
@@ -331,7 +397,7 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait_warp(tfull_bar, 0);
         tc_fence_after();
         if (warp == 2) WJB_STEP_TRACE(6);
-        if (!ln) cluster_wait();  // every CTA of the cluster is running: its shared memory may be written
+        if (!ln_x) cluster_wait();  // every CTA of the cluster is running: its shared memory may be written
         if (q * 32 < p.rows) {
             const uint32_t recv_local = smem_u32(recv);
             const uint32_t qpo = (uint32_t)w / 4;  // float4 groups per owner
@@ -352,7 +418,7 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
         tc_fence_before();
-    } else if (!ln) {
+    } else if (!ln_x) {
         cluster_wait();
     }
     cluster_arrive();
@@ -366,6 +432,15 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int total = p.rows * qpo;
         const int col_base = nt * BN + (int)rank * w;
         const float4* slab = reinterpret_cast<const float4*>(recv);
+        unsigned long long* rowacc = reinterpret_cast<unsigned long long*>(lnbuf);  // fixed-point partial sums of this CTA's columns
+        // rows dividing 128 (the decode batch of 64): a thread meets the same row in every iteration, so it keeps its partial sums in
+        // registers and the 128 / rows threads of a row meet through one shared-memory slot each; other row counts: shared atomics
+        const bool fixed_row = p.out_stats && (128 % p.rows) == 0;
+        long long my_sm = 0, my_sq = 0;
+        if (p.out_stats && !fixed_row) {
+            if (t < p.rows) rowacc[2 * t] = rowacc[2 * t + 1] = 0ull;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         for (int e = t; e < total; e += 128) {
             const int row = e % p.rows, qd = e / p.rows;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -406,6 +481,40 @@ gemm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             oh[0] = __floats2half2_rn(v[0], v[1]);
             oh[1] = __floats2half2_rn(v[2], v[3]);
             *reinterpret_cast<uint2*>(p.out + off) = o;
+            if (p.out_stats) {  // statistics of the values as stored (the next LayerNorm reads the fp16 tensor)
+                // element by element in fixed point: x * 2^20 and x^2 * 2^20 are exact in fp32 for fp16 x, so the sums are exact up to
+                // the 2^-21 rounding of each square -- the variance is then E[x^2] - mean^2 of exact numbers (fp64 in the consumer),
+                // as accurate as a two-pass fp32 LayerNorm even when the row's mean dwarfs its spread
+                const float2 f0 = __half22float2(oh[0]), f1 = __half22float2(oh[1]);
+                const long long sm = __float2ll_rn(f0.x * 1048576.0f) + __float2ll_rn(f0.y * 1048576.0f) + __float2ll_rn(f1.x * 1048576.0f) +
+                                     __float2ll_rn(f1.y * 1048576.0f);
+                const long long sq = __float2ll_rn(f0.x * f0.x * 1048576.0f) + __float2ll_rn(f0.y * f0.y * 1048576.0f) +
+                                     __float2ll_rn(f1.x * f1.x * 1048576.0f) + __float2ll_rn(f1.y * f1.y * 1048576.0f);
+                if (fixed_row) {
+                    my_sm += sm;
+                    my_sq += sq;
+                } else {
+                    atomicAdd(&rowacc[2 * row], (unsigned long long)sm);
+                    atomicAdd(&rowacc[2 * row + 1], (unsigned long long)sq);
+                }
+            }
+        }
+        if (p.out_stats) {
+            if (fixed_row) {  // slot [t]: this thread's partial of row t % rows
+                rowacc[2 * t] = (unsigned long long)my_sm;
+                rowacc[2 * t + 1] = (unsigned long long)my_sq;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (t < p.rows) {
+                unsigned long long a = rowacc[2 * t], b = rowacc[2 * t + 1];
+                if (fixed_row)
+                    for (int u = t + p.rows; u < 128; u += p.rows) {
+                        a += rowacc[2 * u];
+                        b += rowacc[2 * u + 1];
+                    }
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.out_stats) + 2 * t, a);
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.out_stats) + 2 * t + 1, b);
+            }
         }
     }
     __syncthreads();
@@ -484,6 +593,10 @@ static int launch_step_bn(const StepGemmArgs& a, int S, cudaStream_t stream) {
     d.w_early = a.w_constant ? 1 : 0;
     d.ln_g = a.ln_gamma;
     d.ln_b = a.ln_beta;
+    d.ln_stats = a.ln_stats;
+    d.out_stats = a.out_stats;
+    d.pf_ptr = a.prefetch;
+    d.pf_bytes = a.prefetch_bytes;
     d.trace = g_step_trace;
     CUtensorMap tmA, tmB;
     if (int e = encode_a_3d(&tmA, a.A, a.K, a.rows, a.a_row_stride, d.a_tile / 128, d.kpc)) return e;
@@ -564,6 +677,7 @@ int launch_gemm_step(const StepGemmArgs& a, cudaStream_t stream) {
     if ((a.K + kStepBlockK - 1) / kStepBlockK < S) return set_error("gemm_step: K=%d too short for %d slices", a.K, S);
     if (a.out_row_stride % 4) return set_error("gemm_step: output row stride must be a multiple of 4 halfs");
     if ((a.ln_gamma == nullptr) != (a.ln_beta == nullptr)) return set_error("gemm_step: LayerNorm needs both gamma and beta");
+    if (a.ln_stats && !a.ln_gamma) return set_error("gemm_step: row statistics without a LayerNorm");
     switch (bn) {
         case 64: return launch_step_bn<64>(a, S, stream);
         case 128: return launch_step_bn<128>(a, S, stream);

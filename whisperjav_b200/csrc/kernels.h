@@ -87,6 +87,11 @@ struct StepGemmArgs {
     bool w_constant = false;
     const __half* ln_gamma = nullptr;  // LayerNorm over the K columns of A applied inside the kernel (both or neither)
     const __half* ln_beta = nullptr;
+    const long long* ln_stats = nullptr;  // with ln_gamma / ln_beta: [rows][2] fixed-point (x 2^20) sum and sum of squares of every row of A,
+                                          // accumulated by the producers of A (out_stats of an earlier launch / the embedding kernel)
+    long long* out_stats = nullptr;       // [rows][2]: this launch adds the same statistics of the rows it stores (zeroed by the caller)
+    const void* prefetch = nullptr;       // constant bytes (the next Linear's weights) to pull into L2 while this launch runs
+    size_t prefetch_bytes = 0;
 };
 bool gemm_step_supported(int rows, int N, int K);
 int launch_gemm_step(const StepGemmArgs& a, cudaStream_t stream);
@@ -134,8 +139,14 @@ struct CrossCapture {
     long long b_stride = 0, head_stride = 0;
     const int* step = nullptr;
 };
+struct CrossTuning {              // decode-step placement of the cross-attention stream (all off = round-1 behaviour)
+    int early_kv = 0;             // prime the K/V ring before the programmatic-dependent-launch wait (K/V are constants of the run)
+    int evict_first = 0;          // K/V bulk copies carry an L2 evict-first policy
+    const void* pf_ptr = nullptr; // constant bytes (the following Linear's weights) the grid pulls into L2
+    unsigned long long pf_bytes = 0;
+};
 int launch_attn_dec_cross(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T,
-                          cudaStream_t s, int kv_div = 1, const CrossCapture* capture = nullptr);
+                          cudaStream_t s, int kv_div = 1, const CrossCapture* capture = nullptr, const CrossTuning* tuning = nullptr);
 
 // ---- decoder token logic (decode.cu) -------------------------------------------------------
 struct DecodeCtl {            // device-resident control block, one per decode run
@@ -165,7 +176,7 @@ struct DecodeParams {
     float* align_prob = nullptr;
 };
 int launch_embed(const int* tokens, int tokens_stride, const __half* emb, const __half* pos, __half* x, const DecodeCtl* ctl, int B,
-                 int n, cudaStream_t s, long long parity_stride = 0);
+                 int n, cudaStream_t s, long long parity_stride = 0, long long* lnstat = nullptr, int n_sites = 0);
 // beam search state (decode.cu::beam_select_kernel); everything device memory owned by the caller
 constexpr int kMaxBeam = 8;
 struct BeamBufs {

@@ -18,7 +18,7 @@ import ctypes as C
 import math
 import zlib
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Union
+from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -166,14 +166,51 @@ class DecodingResult:
     compression_ratio: float = float("nan")
     language: str = "ja"
     sum_logprob: float = float("nan")
+    complete: bool = True     # False: the run stopped at its step cap before this window had ended (EOT / enough finished beams)
+    steps_needed: int = 0     # sampling steps the window took (its share of a device pass)
 
 
 _DECODE_KEYS = {"task", "language", "temperature", "sample_len", "best_of", "beam_size", "patience", "length_penalty",
                 "prompt", "prefix", "suppress_tokens", "suppress_blank", "without_timestamps", "max_initial_timestamp", "fp16"}
 
 
+class StepCapPlanner:
+    """Two-tier decoding for calls that span several device passes.  A pass costs as many decoder steps as its slowest window, and
+    window lengths are not known in advance; so a first-tier pass is stopped after ``cap`` sampling steps, the windows that have
+    ended by then are final (greedy and beam search at T = 0 are deterministic: stopping the pass does not change them) and the few
+    that have not are pooled and decoded again, from scratch and uncapped, in passes of their own.  With f(c) the share of windows
+    longer than c, a window costs about (c + full * f(c)) / max_batch steps: the planner picks the c that minimises it on the
+    lengths seen so far (first pass uncapped), and keeps passes uncapped when that saves less than 10 %."""
+    CANDIDATES = (8, 12, 16, 24, 32, 48, 64, 96, 128, 160)
+
+    def __init__(self, full: int, min_obs: int = 32):
+        self.full, self.min_obs = int(full), int(min_obs)
+        self.obs: List[int] = []        # steps needed per window seen in a first-tier pass (censored ones count as `full`)
+        self.pass_max: List[int] = []
+
+    def observe(self, results: Sequence["DecodingResult"]) -> None:
+        steps = [r.steps_needed if r.complete else self.full for r in results]
+        if steps:
+            self.obs.extend(steps)
+            self.pass_max.append(max(steps))
+
+    def cap(self) -> Optional[int]:
+        if len(self.obs) < self.min_obs:
+            return None
+        n = float(len(self.obs))
+        best_c, best = None, float(sum(self.pass_max)) / len(self.pass_max) * 0.9
+        for c in self.CANDIDATES:
+            if c >= self.full:
+                break
+            cost = c + self.full * sum(1 for x in self.obs if x > c) / n
+            if cost < best:
+                best_c, best = c, cost
+        return best_c
+
+
 class WhisperB200:
     """Weights resident on one B200 + reusable workspaces; ``transcribe`` mirrors upstream's signature."""
+    tiered_decode = True   # StepCapPlanner for calls with more windows than max_batch (results are identical either way)
 
     def __init__(self, dims: Dims, state_dict: Dict[str, torch.Tensor], device: Union[str, int, torch.device] = "cuda",
                  max_batch: int = 64):
@@ -370,7 +407,8 @@ class WhisperB200:
             results.append(DecodingResult(tokens=ids, text=text, avg_logprob=float(h_slp[b]) / (len(ids) + 1),
                                           no_speech_prob=float(h_nsp[b]), temperature=float(temperature),
                                           compression_ratio=compression_ratio(text) if text else 0.0, language=language,
-                                          sum_logprob=float(h_slp[b])))
+                                          sum_logprob=float(h_slp[b]), complete=len(ids) < sample_len,
+                                          steps_needed=min(len(ids) + 1, sample_len)))
         return results
 
     def decode_trace(self, xa: torch.Tensor, forced_tokens: Optional[Sequence[Sequence[int]]] = None, **kw):
@@ -517,6 +555,7 @@ class WhisperB200:
             h_fin_tok, h_fin_score = fin_tokens.cpu().numpy(), fin_score.cpu().numpy()
             h_fin_len, h_fin_count = fin_len.cpu().numpy(), fin_count.cpu().numpy()
             h_nsp = nsp.cpu().numpy()
+            h_done = audio_done.cpu().numpy()
         self.stats["decode_steps"] += steps.value
         self.stats["windows"] += n_audio
         self.stats["device_passes"] += 1
@@ -527,9 +566,10 @@ class WhisperB200:
             live = [(h_live[a * beam + j, :live_len], float(h_slp[a * beam + j])) for j in range(beam)]
             ids, score = beam_finalize_and_rank(finished, live, beam, n_initial, tok.eot, length_penalty)
             text = detokenize([t for t in ids if t < tok.eot]).strip()
+            need = max([int(h_fin_len[a, k]) for k in range(int(h_fin_count[a]))] + [n_initial]) - n_initial + 1
             results.append(DecodingResult(tokens=ids, text=text, avg_logprob=score / (len(ids) + 1), no_speech_prob=float(h_nsp[a]),
                                           temperature=0.0, compression_ratio=compression_ratio(text) if text else 0.0, language=language,
-                                          sum_logprob=score))
+                                          sum_logprob=score, complete=bool(h_done[a]), steps_needed=min(need, opts.sample_len)))
         return results
 
     # ------------------------------------------------------------------ upstream-shaped API
@@ -595,10 +635,43 @@ class WhisperB200:
         mels = self._clip_mels(arrs, content, pinned_audio)
         _mark("mel")
 
+        full_len = int(decode_options.get("sample_len") or d.n_text_ctx // 2)
+
+        def finish(idx: List[int], xa_rows, sizes_rows: List[int], results: List[DecodingResult]) -> None:
+            """the host half of the seek-loop iteration for the windows of one device pass"""
+            if _record_windows:  # parity tests: what every decoded window returned, before the host logic touches it
+                for j, i in enumerate(idx):
+                    r = results[j]
+                    state[i]["windows"].append({"seek": state[i]["seek"], "size": sizes_rows[j], "tokens": list(r.tokens), "avg_logprob": r.avg_logprob,
+                                                "no_speech_prob": r.no_speech_prob, "temperature": r.temperature})
+            pend = [self._slice(state[i], results[j], tok, sizes_rows[j], no_speech_threshold, logprob_threshold) for j, i in enumerate(idx)]
+            if word_timestamps:
+                self._word_timestamps(xa_rows, pend, sizes_rows, tok, language, task, prepend_punctuations, append_punctuations,
+                                      [state[i] for i in idx])
+            for j, i in enumerate(idx):
+                self._commit(state[i], pend[j], results[j], condition_on_previous_text)
+
+        def decode(xa_rows, idx: List[int], step_cap: Optional[int]):
+            prompts = [state[i]["all_tokens"][state[i]["reset"]:] for i in idx]
+            return self._decode_with_fallback(xa_rows, prompts, temps, best_of, language, task, decode_options,
+                                              compression_ratio_threshold, logprob_threshold, no_speech_threshold, step_cap=step_cap)
+
         while True:
             active = [i for i in range(n) if state[i]["seek"] < content[i]]
             if not active:
                 break
+            planner = None
+            if self.tiered_decode and len(active) > self.max_batch and not decode_options.get("prefix") and temps[0] == 0:
+                planner = StepCapPlanner(full_len, min_obs=min(32, self.max_batch))
+            pool: List[Tuple[int, torch.Tensor, int]] = []   # windows a capped pass left unfinished: (clip, encoder output row, size)
+
+            def flush(k: int) -> None:
+                take, rest = pool[:k], pool[k:]
+                pool[:] = rest
+                idx = [i for i, _, _ in take]
+                xa_p = torch.stack([x for _, x, _ in take])
+                finish(idx, xa_p, [z for _, _, z in take], decode(xa_p, idx, None))
+
             for c0 in range(0, len(active), self.max_batch):
                 chunk = active[c0: c0 + self.max_batch]
                 sizes = [min(N_FRAMES, content[i] - state[i]["seek"]) for i in chunk]
@@ -606,22 +679,26 @@ class WhisperB200:
                 _mark("gather")
                 xa = self.encode(win, reuse="xa_loop")
                 _mark("encode")
-                prompts = [state[i]["all_tokens"][state[i]["reset"]:] for i in chunk]
-                results = self._decode_with_fallback(xa, prompts, temps, best_of, language, task, decode_options,
-                                                     compression_ratio_threshold, logprob_threshold, no_speech_threshold)
+                cap = planner.cap() if planner is not None else None
+                results = decode(xa, chunk, cap)
                 _mark("decode")
-                if _record_windows:  # parity tests: what every decoded window returned, before the host logic touches it
-                    for j, i in enumerate(chunk):
-                        r = results[j]
-                        state[i]["windows"].append({"seek": state[i]["seek"], "size": sizes[j], "tokens": list(r.tokens), "avg_logprob": r.avg_logprob,
-                                                    "no_speech_prob": r.no_speech_prob, "temperature": r.temperature})
-                pend = [self._slice(state[i], results[j], tok, sizes[j], no_speech_threshold, logprob_threshold) for j, i in enumerate(chunk)]
-                if word_timestamps:
-                    self._word_timestamps(xa, pend, sizes, tok, language, task, prepend_punctuations, append_punctuations,
-                                          [state[i] for i in chunk])
-                for j, i in enumerate(chunk):
-                    self._commit(state[i], pend[j], results[j], condition_on_previous_text)
+                if planner is not None:
+                    planner.observe(results)
+                late = [j for j, r in enumerate(results) if not r.complete] if cap is not None else []
+                if late:
+                    self.stats["windows_redecoded"] = self.stats.get("windows_redecoded", 0) + len(late)
+                    pool.extend((chunk[j], xa[j].clone(), sizes[j]) for j in late)
+                    keep = [j for j in range(len(chunk)) if results[j].complete]
+                    if keep:
+                        finish([chunk[j] for j in keep], xa[torch.tensor(keep, device=self.device)].contiguous(), [sizes[j] for j in keep],
+                               [results[j] for j in keep])
+                else:
+                    finish(chunk, xa, sizes, results)
+                while len(pool) >= self.max_batch:
+                    flush(self.max_batch)
                 _mark("advance")
+            if pool:
+                flush(len(pool))
         if _trace:
             import sys
             keys = list(_t)
@@ -675,7 +752,8 @@ class WhisperB200:
             win[j, 1: 1 + z] = mel[i, 1 + s: 1 + s + z]
         return win
 
-    def _decode_with_fallback(self, xa, prompts, temps, best_of, language, task, decode_options, cr_thr, lp_thr, ns_thr):
+    def _decode_with_fallback(self, xa, prompts, temps, best_of, language, task, decode_options, cr_thr, lp_thr, ns_thr,
+                              step_cap: Optional[int] = None):
         """upstream transcribe.py::decode_with_fallback, batched: every window is decoded at temps[0]; windows whose result
         looks degenerate (compression ratio too high, or average log-probability too low unless the window is judged
         silent) are re-decoded as a smaller batch at the next temperature; at T > 0 ``best_of`` samples are drawn per
@@ -690,15 +768,20 @@ class WhisperB200:
             sub_prompts = [prompts[i] for i in todo]
             group = best_of if (t > 0 and best_of > 1) else 1
             cands = []
+            opts_t = decode_options
+            if step_cap is not None and ti == 0 and t == 0:
+                opts_t = dict(decode_options, sample_len=min(int(step_cap), int(decode_options.get("sample_len") or step_cap)))
             for g in range(group):
                 self._sample_calls += 1
-                cands.append(self._decode_with_prompts(sub_xa, sub_prompts, t, language, task, decode_options,
+                cands.append(self._decode_with_prompts(sub_xa, sub_prompts, t, language, task, opts_t,
                                                        seed=0x5EED0000 + 7919 * self._sample_calls))
             still = []
             for k, i in enumerate(todo):
                 opts_k = [c[k] for c in cands]
                 best = max(opts_k, key=lambda r: r.sum_logprob / max(len(r.tokens), 1)) if group > 1 else opts_k[0]
                 final[i] = best
+                if opts_t is not decode_options and not best.complete:
+                    continue   # cut off by the step cap: not a result yet
                 needs = False
                 if cr_thr is not None and best.compression_ratio > cr_thr:
                     needs = True
