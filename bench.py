@@ -308,7 +308,7 @@ def run_ours(args):
         cross_gbs = cross_bytes / (cross_us * 1e-6) / 1e9
         rl_all["decode_cross_attention"] = {
             "kernel": "attn_dec_cross_bulk_kernel", "bound": "hbm", "achieved": cross_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": cross_gbs / peaks["hbm_gbs"], "traffic": 496.5e6, "traffic_source": "profiles/r1d_prof_decode.json (dram read + write per launch, ncu --set full)",
+            "frac": cross_gbs / peaks["hbm_gbs"], "traffic": 495.3e6, "traffic_source": "profiles/r2_prof_decode.json (dram read 491.72 MB + write 3.1-4.0 MB per launch, ncu --set full)",
             "algorithmic_bytes_per_launch": cross_bytes, "us_per_launch": cross_us, "launches_per_decoder_step": dims.n_text_layer,
             "share_of_decode_step": cross_us * 1e-3 * dims.n_text_layer * (active / max(B * steps_run, 1.0)) / (dec_ms / max(steps_run, 1.0)),
             "note": "timed alone with every row alive; inside the step rows that reached EOT are skipped (share scaled by the live-row fraction)"}

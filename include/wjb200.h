@@ -230,6 +230,10 @@ int wjb_attention_encoder_f16(const void* qkv, void* out, int batch, int T, int 
 int wjb_attention_self_f16(const void* qkv, void* kv_cache, void* out, const int32_t* position, int batch, int n_head, int n_ctx,
                            void* stream);
 int wjb_attention_cross_f16(const void* q, const void* kv, void* out, int batch, int n_head, int T, void* stream);
+/* beam search: rows = windows * beams queries, row r attends over the K/V of window r / beams (kv [windows][2 * n_head][T][64]); for
+ * beams <= 4 the beams of a window share one pass over its K/V (upstream repeats the audio features per beam,
+ * whisper/decoding.py::DecodingTask.run `audio_features.repeat_interleave(self.n_group, dim=0)`) */
+int wjb_attention_cross_beam_f16(const void* q, const void* kv, void* out, int rows, int n_head, int T, int beams, void* stream);
 
 /* ---- per-kernel-class timing of wjb_encoder_forward (CUDA events on the launching stream) ------
  * classes: 0 = tcgen05 GEMM (conv1/conv2/linear), 1 = encoder attention, 2 = LayerNorm.  Off by default. */

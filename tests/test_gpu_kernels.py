@@ -336,6 +336,34 @@ def test_attention_cross(lib, B, H, T):
     assert (out.float() - ref).abs().max().item() <= 3e-3
 
 
+@pytest.mark.parametrize("Wn,beams,H,T", [(3, 2, 6, 1500), (64, 2, 20, 1500), (5, 3, 20, 1500), (4, 4, 6, 700), (3, 5, 6, 1500)])
+def test_attention_cross_beams_share_the_window_stream(lib, Wn, beams, H, T):
+    """Beam search: the queries of a window's beams against that window's K/V (one 256-thread CTA streams them once for beams <= 4,
+    beams = 5 falls back to one CTA per row); same math and tolerance as the single-query kernel, identical run to run."""
+    n = 64 * H
+    g = torch.Generator().manual_seed(Wn * 10 + beams)
+    q = (torch.randn(Wn * beams, n, generator=g) * 1.5).half().to(DEV)
+    kv = (torch.randn(Wn, 2 * H, T, 64, generator=g)).half().to(DEV)
+    outs = []
+    for _ in range(2):
+        out = torch.zeros(Wn * beams, n, dtype=torch.float16, device=DEV)
+        _lib.check(lib.wjb_attention_cross_beam_f16(_lib.ptr(q), _lib.ptr(kv), _lib.ptr(out), Wn * beams, H, T, beams, _lib.stream_ptr()), "cross beam")
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    qh = q.float().view(Wn, beams, H, 64).permute(0, 2, 1, 3)                 # [window][head][beam][64]
+    k, v = kv[:, :H].float(), kv[:, H:].float()
+    w = r16(torch.softmax(qh @ k.transpose(-1, -2) * 0.125, -1))
+    ref = (w @ v).permute(0, 2, 1, 3).reshape(Wn * beams, n)
+    assert (outs[0].float() - ref).abs().max().item() <= 3e-3
+    # a window's beams fed one at a time through the single-query kernel: the same numbers up to the fp32 summation order
+    single = torch.zeros(Wn, n, dtype=torch.float16, device=DEV)
+    q0 = q.view(Wn, beams, n)[:, 0].contiguous()
+    _lib.check(lib.wjb_attention_cross_f16(_lib.ptr(q0), _lib.ptr(kv), _lib.ptr(single), Wn, H, T, _lib.stream_ptr()), "cross")
+    torch.cuda.synchronize()
+    assert (outs[0].view(Wn, beams, n)[:, 0].float() - single.float()).abs().max().item() <= 2e-3
+
+
 @pytest.mark.parametrize("n_mels", [80, 128])
 def test_logmel_vs_torch(lib, diag_dir, n_mels):
     """Fused STFT+mel+log kernel vs torch.stft in fp32 (tolerance from north_star: 1e-3 abs)."""

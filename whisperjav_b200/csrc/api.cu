@@ -1184,4 +1184,10 @@ int wjb_attention_cross_f16(const void* q, const void* kv, void* out, int batch,
     return launch_attn_dec_cross((const __half*)q, (const __half*)kv, (__half*)out, nullptr, batch, n_head, T, (cudaStream_t)stream);
 }
 
+int wjb_attention_cross_beam_f16(const void* q, const void* kv, void* out, int rows, int n_head, int T, int beams, void* stream) {
+    if (int e = ensure_init()) return e;
+    if (beams < 1 || rows % beams) return set_error("attention_cross_beam: %d rows is not a multiple of %d beams", rows, beams);
+    return launch_attn_dec_cross((const __half*)q, (const __half*)kv, (__half*)out, nullptr, rows, n_head, T, (cudaStream_t)stream, beams);
+}
+
 }  // extern "C"

@@ -150,9 +150,16 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
                     for (int i = 0; i < 64; ++i)
                         if (hf * 64 + i >= kvalid) s[i] = 0xff800000u;  // -inf: exp2 -> 0
                 }
-                float mx = -INFINITY;
+                // four independent maxima (a 64-deep dependent FMNMX chain costs ~250 cycles per half with two softmax warps per scheduler)
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+                for (int i = 0; i < 64; i += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+                    mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+                    mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+                }
+                const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
                 if (j == 0 && hf == 0) {
                     m_ref = mx;
                 } else {
@@ -190,6 +197,8 @@ attn_encoder_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restric
                     }
                 }
                 const float mb = m_ref * sl2;
+                // two accumulation chains, in this order: the order of these fp32 adds is part of the encoder's bit pattern, which the
+                // model-level parity thresholds were measured on (four chains were tried: not faster, and every downstream tie re-rolled)
                 float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -428,13 +437,18 @@ constexpr int kCrossMaxT = 1536;
 // flight while the softmax runs.
 constexpr int kCbStages = 4, kCbKeys = 128, kCbStageBytes = kCbKeys * 128;
 constexpr int kCbMaxQ = 4;  // queries (beams of one window) that may share one pass over the window's K/V
-constexpr int cb_smem_bytes(int nq) { return kCbStages * kCbStageBytes + nq * kCrossMaxT * 4 + 64 * 4 + 4 * 64 * 4 + 64; }
+// threads per CTA: 128 for one query; the beam-search instances (NQ >= 2) do NQ times the arithmetic per streamed byte and were
+// latency-bound with 2 CTAs x 4 warps per SM (140 us vs 80 us per launch at NQ = 2, profiles/r2_launches.md): they run 8 warps
+constexpr int cb_threads(int nq) { return nq == 1 ? 128 : 256; }
+// ring depth: 4 stages for one query; 3 for the beam instances so that three 256-thread CTAs still fit one SM (62.6 KB at NQ = 2)
+constexpr int cb_stages(int nq) { return nq == 1 ? kCbStages : 3; }
+constexpr int cb_smem_bytes(int nq) { return cb_stages(nq) * kCbStageBytes + nq * kCrossMaxT * 4 + 64 * 4 + (cb_threads(nq) / 32) * 64 * 4 + 64; }
 constexpr int kCbSmem = cb_smem_bytes(1);
 
 // NQ = 1: one CTA per (row, head); with beam search either the row reads the K/V of window row / kv_div (any beam size), or
 // NQ = beam_size queries of one window share the CTA and the window's K/V stream through shared memory once (blockIdx.y = window).
 template <int NQ>
-__global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
+__global__ void __launch_bounds__(cb_threads(NQ)) attn_dec_cross_bulk_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
                                                                              __half* __restrict__ out,
                                                                              const unsigned char* __restrict__ done, int H, int T, int kv_div,
                                                                              const CrossCapture cap, const CrossTuning tune) {
@@ -448,11 +462,13 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
     const int row0 = b * NQ;  // first query row of this CTA
     if (done && done[row0]) return;  // the beams of a window finish together
     extern __shared__ __align__(128) uint8_t cb_smem[];
+    constexpr int ST = cb_stages(NQ);
     uint8_t* ring = cb_smem;
-    float* sc = reinterpret_cast<float*>(cb_smem + kCbStages * kCbStageBytes);  // [NQ][kCrossMaxT]
+    float* sc = reinterpret_cast<float*>(cb_smem + ST * kCbStageBytes);  // [NQ][kCrossMaxT]
     float* red = sc + NQ * kCrossMaxT;
-    float* osum = red + 64;                      // [4][64]
-    uint64_t* full = reinterpret_cast<uint64_t*>(osum + 4 * 64);
+    constexpr int TH = cb_threads(NQ), W = TH / 32, kSlots = TH / 8;  // key rows in flight per pass: one per 8 lanes
+    float* osum = red + 64;                      // [W][64]
+    uint64_t* full = reinterpret_cast<uint64_t*>(osum + W * 64);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = H * 64;
     const int bk = (NQ > 1) ? b : b / kv_div;  // window whose K/V this CTA reads
@@ -464,7 +480,7 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
     auto chunk_src = [&](int c) { return (c < nck ? Kg : Vg) + (size_t)(c % nck) * kCbStageBytes; };
     auto chunk_keys = [&](int c) { return min(kCbKeys, T - (c % nck) * kCbKeys); };
     auto issue = [&](int c) {
-        const int st = c % kCbStages;
+        const int st = c % ST;
         const uint32_t bytes = chunk_keys(c) * 128;
         mbar_arrive_expect_tx(&full[st], bytes);
         if (tune.evict_first) {  // the K/V stream is read once per step: do not let it push the layer's weights out of L2
@@ -480,15 +496,15 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
         }
     };
     if (tid == 0) {
-        for (int i = 0; i < kCbStages; ++i) mbar_init(&full[i], 1);
+        for (int i = 0; i < ST; ++i) mbar_init(&full[i], 1);
         fence_barrier_init();
     }
     __syncthreads();
     if (tid == 0)
-        for (int c = 0; c < kCbStages && c < total; ++c) issue(c);
+        for (int c = 0; c < ST && c < total; ++c) issue(c);
     if (tune.early_kv) asm volatile("griddepcontrol.wait;" ::: "memory");  // q (and `out`) belong to the chain
 
-    const int chunk16 = tid & 7, slot = tid >> 3;  // 16 key slots x 8 sixteen-byte pieces
+    const int chunk16 = tid & 7, slot = tid >> 3;  // kSlots key slots x 8 sixteen-byte pieces
     float qf[NQ][8];
 #pragma unroll
     for (int i = 0; i < NQ; ++i) {
@@ -510,15 +526,15 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
 #pragma unroll
     for (int i = 0; i < NQ; ++i) inv[i] = 0.f;
     for (int c = 0; c < total; ++c) {
-        const int st = c % kCbStages;
-        mbar_wait(&full[st], (c / kCbStages) & 1);
+        const int st = c % ST;
+        mbar_wait(&full[st], (c / ST) & 1);
         const uint8_t* base = ring + st * kCbStageBytes;
         const int keys = chunk_keys(c);
         const int key0 = (c % nck) * kCbKeys;
         if (c < nck) {
 #pragma unroll
-            for (int it = 0; it < kCbKeys / 16; ++it) {
-                const int k = it * 16 + slot;
+            for (int it = 0; it < kCbKeys / kSlots; ++it) {
+                const int k = it * kSlots + slot;
                 const uint4 u = *reinterpret_cast<const uint4*>(base + k * 128 + chunk16 * 16);
                 const __half2* h2 = reinterpret_cast<const __half2*>(&u);
                 float kf[8];
@@ -541,8 +557,8 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
             }
         } else {
 #pragma unroll
-            for (int it = 0; it < kCbKeys / 16; ++it) {
-                const int k = it * 16 + slot;
+            for (int it = 0; it < kCbKeys / kSlots; ++it) {
+                const int k = it * kSlots + slot;
                 const uint4 u = (k < keys) ? *reinterpret_cast<const uint4*>(base + k * 128 + chunk16 * 16) : make_uint4(0, 0, 0, 0);
                 const __half2* h2 = reinterpret_cast<const __half2*>(&u);
                 float vf[8];
@@ -561,35 +577,40 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
             }
         }
         __syncthreads();  // stage consumed by everyone (and, after the last K chunk, all scores are in smem)
-        if (tid == 0 && c + kCbStages < total) issue(c + kCbStages);
+        if (tid == 0 && c + ST < total) issue(c + ST);
         if (c == nck - 1) {
             if (NQ == 1 && cap.base) {
                 // word-timestamp alignment pass: the scaled scores q.k / sqrt(d) of this (row, head, position), fp16 as the
                 // reference's fp16 attention matmul returns them (timing.py collects them through forward hooks)
                 __half* dst = cap.base + (long long)b * cap.b_stride + (long long)h * cap.head_stride + (long long)(*cap.step) * T;
-                for (int t = tid; t < T; t += kCrossThreads) dst[t] = __float2half_rn(sc[t]);
+                for (int t = tid; t < T; t += TH) dst[t] = __float2half_rn(sc[t]);
             }
             // softmax over the T scores of every query (V chunks are already streaming into the ring)
 #pragma unroll
             for (int i = 0; i < NQ; ++i) {
                 float* sci = sc + i * kCrossMaxT;
                 float mx = -INFINITY;
-                for (int t = tid; t < T; t += kCrossThreads) mx = fmaxf(mx, sci[t]);
+                for (int t = tid; t < T; t += TH) mx = fmaxf(mx, sci[t]);
                 mx = warp_max(mx);
                 if (i > 0) __syncthreads();  // red[] of the previous query has been read
                 if (lane == 0) red[warp] = mx;
                 __syncthreads();
-                mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+                mx = red[0];
+#pragma unroll
+                for (int w_ = 1; w_ < W; ++w_) mx = fmaxf(mx, red[w_]);
                 float sum = 0.f;
-                for (int t = tid; t < T; t += kCrossThreads) {
+                for (int t = tid; t < T; t += TH) {
                     const float e = __expf(sci[t] - mx);
                     sci[t] = e;
                     sum += e;
                 }
                 sum = warp_sum(sum);
-                if (lane == 0) red[4 + warp] = sum;
+                if (lane == 0) red[W + warp] = sum;
                 __syncthreads();
-                inv[i] = 1.0f / (red[4] + red[5] + red[6] + red[7]);
+                float tot = red[W];
+#pragma unroll
+                for (int w_ = 1; w_ < W; ++w_) tot += red[W + w_];
+                inv[i] = 1.0f / tot;
             }
         }
     }
@@ -606,8 +627,12 @@ __global__ void __launch_bounds__(kCrossThreads) attn_dec_cross_bulk_kernel(cons
             for (int j = 0; j < 8; ++j) osum[warp * 64 + lane * 8 + j] = acc[i][j];
         }
         __syncthreads();
-        if (tid < 64)
-            out[(long long)(row0 + i) * n + h * 64 + tid] = __float2half_rn(osum[tid] + osum[64 + tid] + osum[128 + tid] + osum[192 + tid]);
+        if (tid < 64) {
+            float v = osum[tid];
+#pragma unroll
+            for (int w_ = 1; w_ < W; ++w_) v += osum[w_ * 64 + tid];
+            out[(long long)(row0 + i) * n + h * 64 + tid] = __float2half_rn(v);
+        }
     }
 }
 
@@ -615,7 +640,7 @@ template <int NQ>
 static int launch_cross_bulk(const __half* q, const __half* kv, __half* out, const unsigned char* done, int B, int H, int T, int kv_div,
                              cudaStream_t s, const CrossCapture& cap, const CrossTuning& tune) {
     dim3 grid(H, B / NQ);
-    cudaError_t e = launch_k(attn_dec_cross_bulk_kernel<NQ>, grid, dim3(kCrossThreads), (size_t)cb_smem_bytes(NQ), s, q, kv, out, done, H, T, kv_div, cap,
+    cudaError_t e = launch_k(attn_dec_cross_bulk_kernel<NQ>, grid, dim3(cb_threads(NQ)), (size_t)cb_smem_bytes(NQ), s, q, kv, out, done, H, T, kv_div, cap,
                              tune);
     if (e != cudaSuccess) return set_error("attn_dec_cross_bulk launch: %s", cudaGetErrorString(e));
     return 0;
