@@ -211,6 +211,7 @@ class StepCapPlanner:
 class WhisperB200:
     """Weights resident on one B200 + reusable workspaces; ``transcribe`` mirrors upstream's signature."""
     tiered_decode = True   # StepCapPlanner for calls with more windows than max_batch (results are identical either way)
+    trace_timing = False   # transcribe_batch prints per-stage wall times (adds a device synchronisation after every stage)
 
     def __init__(self, dims: Dims, state_dict: Dict[str, torch.Tensor], device: Union[str, int, torch.device] = "cuda",
                  max_batch: int = 64):
@@ -622,8 +623,8 @@ class WhisperB200:
         for st in state:
             st["reset"] = 0
 
-        import os, time
-        _trace = os.environ.get("WJB_TIMING") == "1"
+        import time
+        _trace = bool(self.trace_timing)   # diagnostic: per-stage wall times of this call on stderr (synchronises after every stage)
         _t = {"t0": time.perf_counter()}
 
         def _mark(name):
