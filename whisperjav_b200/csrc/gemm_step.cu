@@ -20,7 +20,9 @@
 //     runs inside: every CTA holds a K slice of all rows, so the cluster adds per-row partial sums through distributed
 //     shared memory (two passes: mean, then sum of squared deviations, fp32, rank order), normalises its tile in place
 //     and hands it to the MMA thread -- one launch and one global round trip less per LayerNorm,
-//   * ... or, in the decode step, without any exchange: the GEMM that PRODUCES the residual stream (out / cross-out / fc2) adds
+//   * ... or without any exchange (decode-step option 1 of wjb_debug_set_decode_flags; correct, tested, measured no faster than the
+//     separate LayerNorm launch and therefore off by default -- DESIGN.md section 4): the GEMM that PRODUCES the residual stream
+//     (out / cross-out / fc2) adds
 //     per-row sum and sum of squares of the fp16 values it stores to a fixed-point accumulator (64-bit integer atomics: the
 //     order of the adds cannot change the result), and the GEMM behind the LayerNorm reads two integers per row, normalises
 //     its tile in shared memory with the reference's rounding points (fp32 statistics of the fp16 row, fp16-rounded output)
