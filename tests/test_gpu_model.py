@@ -246,8 +246,8 @@ def test_upstream_transcribe_keywords_are_accepted(tiny, clips):
 
 @pytest.mark.parametrize("mode", ["greedy", "beam", "words"])
 def test_two_tier_decoding_does_not_change_results(tiny, mode, monkeypatch):
-    """More windows than ``max_batch``: first-tier passes stop at a step cap, unfinished windows are pooled and decoded again
-    (StepCapPlanner).  Everything a caller sees -- tokens, segment times, word times, probabilities -- must equal the single-tier
+    """More windows than ``max_batch``: first-tier passes stop at a step cap, unfinished windows are pooled and decoded again, the
+    second tier capped too, a third to the end (StepCapPlanner / TierScheduler).  Everything a caller sees -- tokens, segment times, word times, probabilities -- must equal the single-tier
     run bit for bit, and the capped run must really have cut windows off."""
     dims, w, m, pw = tiny
     many = [speech_shaped_audio(4.0 + 1.7 * (i % 9), 7000 + i) for i in range(27)]
@@ -261,7 +261,8 @@ def test_two_tier_decoding_does_not_change_results(tiny, mode, monkeypatch):
     plain = m.transcribe_batch(many, **kw)
     steps_plain = m.stats["decode_steps"]
     monkeypatch.setattr(M.WhisperB200, "tiered_decode", True)
-    monkeypatch.setattr(M.StepCapPlanner, "cap", lambda self: 12 if self.obs else None)   # force a low cap after the first pass
+    # force low caps after the first pass: tier 1 stops at 12 steps, tier 2 at 40, tier 3 runs to the end
+    monkeypatch.setattr(M.StepCapPlanner, "cap", lambda self, tier=0: ((12, 40)[tier] if tier < 2 else None) if self.obs else None)
     before = m.stats.get("windows_redecoded", 0)
     tiered = m.transcribe_batch(many, **kw)
     assert m.stats.get("windows_redecoded", 0) > before

@@ -118,19 +118,74 @@ def test_step_cap_keeps_cut_off_windows_out_of_the_ladder():
     assert [o.tokens for o in out2] == [[5, 6, 7], list(range(100, 140)), list(range(30))] and out2[0].tokens == out[0].tokens
 
 
-def test_step_cap_planner_picks_the_cheapest_cap_and_stays_off_when_it_does_not_pay():
+def test_step_cap_planner_picks_the_cheapest_ladder_and_stays_off_when_it_does_not_pay():
     mk = lambda n, done=True: M.DecodingResult(tokens=[1] * n, complete=done, steps_needed=n)   # noqa: E731
     p = M.StepCapPlanner(full=224, min_obs=32)
-    assert p.cap() is None                                  # nothing seen yet: first pass runs uncapped
+    assert p.ladder() == [] and p.cap() is None             # nothing seen yet: first pass runs uncapped
     p.observe([mk(20 + (k % 10)) for k in range(60)] + [mk(224) for _ in range(4)])   # 6 % stragglers at the limit
-    c = p.cap()
-    assert c == 32                                          # 32 + 224 * 4/64 = 46 steps per pass instead of 224
+    assert p.ladder() == [32] and p.cap() == 32 and p.cap(1) is None   # 32 + 232 * 4/64 = 46.5 steps per pass instead of 224; no middle tier pays
     q = M.StepCapPlanner(full=224, min_obs=32)
     q.observe([mk(200 + (k % 20)) for k in range(64)])      # everything long: capping buys nothing
-    assert q.cap() is None
-    r = M.StepCapPlanner(full=224, min_obs=32)
-    r.observe([mk(16, done=False) for _ in range(40)] + [mk(10) for _ in range(24)])  # censored windows count as full length
-    assert r.cap() is None or r.cap() >= 8
+    assert q.ladder() == []
     u = M.StepCapPlanner(full=224, min_obs=32)
     u.observe([mk(30) for _ in range(64)])                  # uniform lengths: the pass already ends at 30
-    assert u.cap() is None
+    assert u.ladder() == []
+    # a long middle: 70 % short, 25 % around 80-90, 5 % never end -> two caps
+    t = M.StepCapPlanner(full=224, min_obs=32)
+    t.observe([mk(10 + (k % 6)) for k in range(90)] + [mk(80 + (k % 10)) for k in range(32)] + [mk(224) for _ in range(6)])
+    lad = t.ladder()
+    assert len(lad) == 2 and lad[0] == 16 and lad[1] == 96, lad
+    o = t.PASS_OVERHEAD
+    one = min(c + (224 + o) * t._share_longer(c) for c in t.CANDIDATES)
+    two = lad[0] + t._share_longer(lad[0]) * (lad[1] + o) + t._share_longer(lad[1]) * (224 + o)
+    assert two < 0.97 * one
+    # windows cut off count as full until a later tier tells their length
+    r = M.StepCapPlanner(full=224, min_obs=32)
+    r.observe([mk(10) for _ in range(48)] + [mk(16, done=False) for _ in range(16)])
+    assert r.cut == 16 and r.obs.count(224) == 16
+    r.resolve([mk(60) for _ in range(10)] + [mk(96, done=False) for _ in range(2)])
+    assert r.cut == 6 and r.obs.count(224) == 6 and r.obs.count(60) == 10
+
+
+def test_tier_scheduler_finishes_every_window_once_with_its_full_result():
+    """Scripted device: window i needs L[i] steps; a pass costs max(min(L, cap)) steps.  Every window must be finished exactly once with
+    the tokens an uncapped decode gives, the pools must drain, and the run must cost fewer steps than one-tier decoding."""
+    import random
+    rnd = random.Random(3)
+    n, B, full = 640, 64, 224
+    L = [rnd.choice([8, 9, 11, 14, 20, 26]) if rnd.random() < 0.72 else (rnd.randint(60, 100) if rnd.random() < 0.8 else full) for _ in range(n)]
+    cost = {"steps": 0, "passes": 0}
+    done = {}
+
+    def decode(rows, idx, cap):
+        assert rows.shape[0] == len(idx) and [int(v) for v in rows[:, 0].tolist()] == idx   # the encoder rows travel with their windows
+        lim = full if cap is None else cap
+        cost["steps"] += max(min(L[i], lim) for i in idx)
+        cost["passes"] += 1
+        return [M.DecodingResult(tokens=[i] * min(L[i] - 1, lim), complete=(L[i] <= lim) if cap is not None else True, steps_needed=min(L[i], lim))
+                for i in idx]
+
+    def finish(idx, rows, sizes, results):
+        for i, z, r in zip(idx, sizes, results):
+            assert i not in done and z == 100 + i and r.complete
+            done[i] = r.tokens
+
+    stats = {}
+    sched = M.TierScheduler(M.StepCapPlanner(full, min_obs=32), B, decode, finish, stats)
+    for c0 in range(0, n, B):
+        idx = list(range(c0, c0 + B))
+        sched.submit(idx, torch.tensor(idx, dtype=torch.float32).view(-1, 1).repeat(1, 3), [100 + i for i in idx])
+    sched.drain()
+    assert sorted(done) == list(range(n)) and all(done[i] == [i] * (L[i] - 1) for i in range(n))
+    assert all(not p for p in sched.pools.values())
+    one_tier = sum(max(L[c0: c0 + B]) for c0 in range(0, n, B))
+    assert stats["windows_redecoded"] > 0 and cost["steps"] < 0.7 * one_tier, (cost, one_tier, stats)
+    # no planner: plain passes
+    done.clear()
+    cost.update(steps=0, passes=0)
+    plain = M.TierScheduler(None, B, decode, finish, {})
+    for c0 in range(0, n, B):
+        idx = list(range(c0, c0 + B))
+        plain.submit(idx, torch.tensor(idx, dtype=torch.float32).view(-1, 1).repeat(1, 3), [100 + i for i in idx])
+    plain.drain()
+    assert cost["steps"] == one_tier and cost["passes"] == n // B and sorted(done) == list(range(n))

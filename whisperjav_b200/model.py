@@ -175,37 +175,116 @@ _DECODE_KEYS = {"task", "language", "temperature", "sample_len", "best_of", "bea
 
 
 class StepCapPlanner:
-    """Two-tier decoding for calls that span several device passes.  A pass costs as many decoder steps as its slowest window, and
-    window lengths are not known in advance; so a first-tier pass is stopped after ``cap`` sampling steps, the windows that have
+    """Tiered decoding for calls that span several device passes.  A pass costs as many decoder steps as its slowest window, and
+    window lengths are not known in advance; so a first-tier pass is stopped after ``c1`` sampling steps, the windows that have
     ended by then are final (greedy and beam search at T = 0 are deterministic: stopping the pass does not change them) and the few
-    that have not are pooled and decoded again, from scratch and uncapped, in passes of their own.  With f(c) the share of windows
-    longer than c, a window costs about (c + full * f(c)) / max_batch steps: the planner picks the c that minimises it on the
-    lengths seen so far (first pass uncapped), and keeps passes uncapped when that saves less than 10 %."""
+    that have not are pooled and decoded again, from scratch, in passes of their own -- stopped in turn at ``c2``, whose leftovers
+    run uncapped in a last tier.  With f(c) the share of windows longer than c, a window costs about
+    (c1 + f(c1) (c2 + o) + f(c2) (full + o)) / max_batch steps (o = the fixed cost of a pass): the planner picks the ladder (no cap, [c1] or [c1, c2]) that minimises it on the
+    lengths seen so far (the first pass runs uncapped; a window cut off counts as ``full`` until a later tier tells its length), and
+    keeps passes uncapped when that saves less than 10 %."""
     CANDIDATES = (8, 12, 16, 24, 32, 48, 64, 96, 128, 160)
+    PASS_OVERHEAD = 8   # what a device pass costs besides its decoder steps (cross-K/V projection, graph capture, read-back), in steps
 
     def __init__(self, full: int, min_obs: int = 32):
         self.full, self.min_obs = int(full), int(min_obs)
-        self.obs: List[int] = []        # steps needed per window seen in a first-tier pass (censored ones count as `full`)
+        self.obs: List[int] = []        # steps needed per window of the first tier (a window cut off counts as `full` ...)
+        self.cut = 0                    # ... and is counted here until resolve() replaces it by its length
         self.pass_max: List[int] = []
 
     def observe(self, results: Sequence["DecodingResult"]) -> None:
+        """the results of a first-tier pass"""
         steps = [r.steps_needed if r.complete else self.full for r in results]
         if steps:
             self.obs.extend(steps)
+            self.cut += sum(1 for r in results if not r.complete)
             self.pass_max.append(max(steps))
 
-    def cap(self) -> Optional[int]:
+    def resolve(self, results: Sequence["DecodingResult"]) -> None:
+        """windows of a later tier that have ended: their lengths replace as many ``full`` placeholders"""
+        for r in results:
+            if r.complete and self.cut > 0:
+                self.obs.remove(self.full)
+                self.obs.append(min(int(r.steps_needed), self.full))
+                self.cut -= 1
+
+    def _share_longer(self, c: int) -> float:
+        return sum(1 for x in self.obs if x > c) / float(len(self.obs))
+
+    def ladder(self) -> List[int]:
         if len(self.obs) < self.min_obs:
-            return None
-        n = float(len(self.obs))
-        best_c, best = None, float(sum(self.pass_max)) / len(self.pass_max) * 0.9
-        for c in self.CANDIDATES:
-            if c >= self.full:
-                break
-            cost = c + self.full * sum(1 for x in self.obs if x > c) / n
-            if cost < best:
-                best_c, best = c, cost
-        return best_c
+            return []
+        best: List[int] = []
+        best_cost = float(sum(self.pass_max)) / len(self.pass_max) * 0.9
+        cands = [c for c in self.CANDIDATES if c < self.full]
+        share = {c: self._share_longer(c) for c in cands}
+        o = self.PASS_OVERHEAD
+        for i, c1 in enumerate(cands):
+            cost = c1 + share[c1] * (self.full + o)
+            if cost < best_cost:
+                best, best_cost = [c1], cost
+            for c2 in cands[i + 1:]:
+                cost = c1 + share[c1] * (c2 + o) + share[c2] * (self.full + o)
+                if cost < best_cost * 0.97:   # a third tier has to pay for more than the model sees
+                    best, best_cost = [c1, c2], cost
+        return best
+
+    def cap(self, tier: int = 0) -> Optional[int]:
+        lad = self.ladder()
+        return lad[tier] if tier < len(lad) else None
+
+
+class TierScheduler:
+    """The pass bookkeeping of tiered decoding, free of device specifics: ``decode(rows, idx, cap) -> results`` runs one device pass
+    over the given encoder rows (``cap`` sampling steps at most, None = to the end), ``finish(idx, rows, sizes, results)`` consumes the
+    windows that have ended.  Windows a capped pass cut off wait, with their encoder rows, in the pool of the next tier; a pool is
+    decoded as soon as it holds a full batch, and ``drain()`` empties the pools in tier order."""
+    MAX_CAPPED_TIERS = 2   # whatever the planner says, the third tier runs to the end: every window finishes
+
+    def __init__(self, planner: Optional[StepCapPlanner], max_batch: int, decode, finish, stats: Optional[dict] = None):
+        self.planner, self.max_batch, self.decode, self.finish = planner, int(max_batch), decode, finish
+        self.pools: Dict[int, List[Tuple[int, torch.Tensor, int]]] = {}
+        self.stats = stats if stats is not None else {}
+
+    def _run(self, tier: int, idx: List[int], rows: torch.Tensor, sizes: List[int]) -> None:
+        cap = self.planner.cap(tier) if (self.planner is not None and tier < self.MAX_CAPPED_TIERS) else None
+        results = self.decode(rows, idx, cap)
+        if self.planner is not None:
+            if tier == 0:
+                self.planner.observe(results)
+            else:
+                self.planner.resolve(results)
+        late = [j for j, r in enumerate(results) if not r.complete] if cap is not None else []
+        if not late:
+            self.finish(idx, rows, sizes, results)
+            return
+        self.stats["windows_redecoded"] = self.stats.get("windows_redecoded", 0) + len(late)
+        self.pools.setdefault(tier + 1, []).extend((idx[j], rows[j].clone(), sizes[j]) for j in late)
+        keep = [j for j in range(len(idx)) if results[j].complete]
+        if keep:
+            self.finish([idx[j] for j in keep], rows[torch.tensor(keep, device=rows.device)].contiguous(), [sizes[j] for j in keep],
+                        [results[j] for j in keep])
+
+    def _flush(self, tier: int, k: int) -> None:
+        pool = self.pools[tier]
+        take, self.pools[tier] = pool[:k], pool[k:]
+        self._run(tier, [i for i, _, _ in take], torch.stack([x for _, x, _ in take]), [z for _, _, z in take])
+
+    def submit(self, idx: List[int], rows: torch.Tensor, sizes: List[int]) -> None:
+        """one first-tier pass, then every pool that has filled up"""
+        self._run(0, idx, rows, sizes)
+        tier = 1
+        while tier in self.pools:
+            while len(self.pools[tier]) >= self.max_batch:
+                self._flush(tier, self.max_batch)
+            tier += 1
+
+    def drain(self) -> None:
+        tier = 1
+        while tier in self.pools:
+            while self.pools[tier]:
+                self._flush(tier, min(len(self.pools[tier]), self.max_batch))
+            tier += 1
 
 
 class WhisperB200:
@@ -664,15 +743,7 @@ class WhisperB200:
             planner = None
             if self.tiered_decode and len(active) > self.max_batch and not decode_options.get("prefix") and temps[0] == 0:
                 planner = StepCapPlanner(full_len, min_obs=min(32, self.max_batch))
-            pool: List[Tuple[int, torch.Tensor, int]] = []   # windows a capped pass left unfinished: (clip, encoder output row, size)
-
-            def flush(k: int) -> None:
-                take, rest = pool[:k], pool[k:]
-                pool[:] = rest
-                idx = [i for i, _, _ in take]
-                xa_p = torch.stack([x for _, x, _ in take])
-                finish(idx, xa_p, [z for _, _, z in take], decode(xa_p, idx, None))
-
+            sched = TierScheduler(planner, self.max_batch, decode, finish, self.stats)
             for c0 in range(0, len(active), self.max_batch):
                 chunk = active[c0: c0 + self.max_batch]
                 sizes = [min(N_FRAMES, content[i] - state[i]["seek"]) for i in chunk]
@@ -680,26 +751,9 @@ class WhisperB200:
                 _mark("gather")
                 xa = self.encode(win, reuse="xa_loop")
                 _mark("encode")
-                cap = planner.cap() if planner is not None else None
-                results = decode(xa, chunk, cap)
-                _mark("decode")
-                if planner is not None:
-                    planner.observe(results)
-                late = [j for j, r in enumerate(results) if not r.complete] if cap is not None else []
-                if late:
-                    self.stats["windows_redecoded"] = self.stats.get("windows_redecoded", 0) + len(late)
-                    pool.extend((chunk[j], xa[j].clone(), sizes[j]) for j in late)
-                    keep = [j for j in range(len(chunk)) if results[j].complete]
-                    if keep:
-                        finish([chunk[j] for j in keep], xa[torch.tensor(keep, device=self.device)].contiguous(), [sizes[j] for j in keep],
-                               [results[j] for j in keep])
-                else:
-                    finish(chunk, xa, sizes, results)
-                while len(pool) >= self.max_batch:
-                    flush(self.max_batch)
-                _mark("advance")
-            if pool:
-                flush(len(pool))
+                sched.submit(chunk, xa, sizes)
+                _mark("decode+advance")
+            sched.drain()
         if _trace:
             import sys
             keys = list(_t)
