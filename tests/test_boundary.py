@@ -87,6 +87,9 @@ def test_registration_with_reference_factories(monkeypatch):
         assert isinstance(det, SceneDetector) and det.name == "b200-auditok"
         assert det._config.max_duration == 20.0 and det._config.pass2_max_duration == 19.0 and det._config.pass2_max_silence == 0.5
         assert SceneDetectorFactory.is_backend_available("b200-auditok") == (True, "")
+        sil = SceneDetectorFactory.create("b200-silero", silero_threshold=0.1)
+        assert isinstance(sil, SceneDetector) and sil.name == "b200-silero"
+        assert sil._silero_config.max_duration == 420.0 and sil._silero_config.brute_force_chunk_s == 29.0 and sil._silero_config.silero_threshold == 0.1
         from whisperjav.modules.speech_segmentation import SpeechSegmenterFactory
         from whisperjav.modules.speech_segmentation.base import SpeechSegmenter
         from whisperjav.modules.subtitle_pipeline.generators.factory import TextGeneratorFactory

@@ -107,3 +107,51 @@ def test_detector_needs_a_gpu_and_registers_with_the_reference_factory():
         from whisperjav_b200._lib import WjbError
         with pytest.raises(WjbError):
             det.detect(np.zeros(16000, dtype=np.float32), 16000)
+
+
+# ---- Silero-style detector: energy pass 1 + VAD pass 2 ----------------------------------------------------------------------------
+
+SILERO_KATS = {k["name"]: k for k in json.loads((Path(__file__).parent / "golden" / "reference_silero_scene_kats.json").read_text())}
+
+
+class FakeVad:
+    """stands in for vad.VadB200 with the same call shape: probs(audio [B, S], n_samples [B]) -> [B, windows]"""
+    device = "cpu"
+
+    def probs(self, audio, n_samples):
+        import torch
+        from scene_cases import fake_vad_probs
+        rows = [fake_vad_probs(audio[i, : int(n_samples[i])].numpy()) for i in range(audio.shape[0])]
+        out = torch.zeros(len(rows), (audio.shape[1] + 511) // 512)
+        for i, r in enumerate(rows):
+            out[i, : len(r)] = torch.from_numpy(r)
+        return out
+
+
+def test_silero_style_detector_reproduces_the_reference_driver():
+    """SileroSceneDetector.detect_scenes of the reference (run with a fake VAD, tests/golden/make_silero_scene_kats.py) against
+    B200SileroSceneDetector with the same fake VAD and the numpy twin of the energy kernel: config derivation, which chapters reach
+    pass 2, scenes, the brute-force fall-through, the VAD-segment metadata."""
+    from scene_cases import SILERO_CASES
+    for case in SILERO_CASES:
+        audio, sr = build_case(case)
+        det = SC.B200SileroSceneDetector(vad=FakeVad(), **case.get("kwargs", {}))
+        kat = SILERO_KATS[case["name"]]
+        cfg = det._silero_config
+        assert {"max_duration": cfg.max_duration, "pass2_max_duration": cfg.pass2_max_duration, "brute_force_chunk_s": cfg.brute_force_chunk_s,
+                "min_duration": cfg.min_duration, "silero_threshold": cfg.silero_threshold, "assist_processing": cfg.assist_processing} == kat["config"]
+        det._vad_segments = []
+        scenes, story, counters = SC.two_pass(det._config, len(audio), sr, _numpy_energy(audio), det._fine_split(audio, sr))
+        assert [[s.start_sec, s.end_sec, s.detection_pass, s.metadata.get("split_method", "")] for s in scenes] == kat["scenes"], case["name"]
+        assert [[round(a, 3), round(b, 3)] for a, b in story] == kat["coarse"]
+        assert (det._vad_segments or None) == kat["vad_segments"]
+    assert SC.B200SileroSceneDetector(vad=FakeVad()).name == "b200-silero"
+
+
+def test_hysteresis_takes_an_explicit_negative_threshold():
+    from whisperjav_b200 import hostlogic as H
+    p = np.array([0.0] * 10 + [0.5] * 30 + [0.12] * 30 + [0.5] * 30 + [0.0] * 40, dtype=np.float32)
+    kw = dict(frame_ms=32.0, threshold=0.3, min_speech_duration_ms=100, min_silence_duration_ms=320, speech_pad_ms=0)
+    one = H.probs_to_regions(p, len(p) * 0.032, **kw)                        # default offset threshold 0.15: 0.12 is silence -> two regions
+    two = H.probs_to_regions(p, len(p) * 0.032, neg_threshold=0.1, **kw)     # 0.12 stays speech -> one region
+    assert len(one) == 2 and len(two) == 1

@@ -31,6 +31,8 @@ def register() -> dict:
         from whisperjav.modules.scene_detection_backends import factory as scf  # type: ignore
         scf._BACKEND_REGISTRY["b200-auditok"] = "whisperjav_b200.scenes.B200SceneDetector"
         scf._BACKEND_DEPENDENCIES["b200-auditok"] = {"packages": [], "install_hint": "", "always_available": True}
+        scf._BACKEND_REGISTRY["b200-silero"] = "whisperjav_b200.scenes.B200SileroSceneDetector"
+        scf._BACKEND_DEPENDENCIES["b200-silero"] = {"packages": [], "install_hint": "", "always_available": True}
         done["scene_detector"] = True
     except Exception:
         pass

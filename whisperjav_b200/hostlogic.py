@@ -102,16 +102,16 @@ def pad_and_clamp(timestamps: Sequence[Dict[str, int]], n_audio: int, start_pad:
 
 def probs_to_regions(probs: Sequence[float], audio_duration_sec: float, *, frame_ms: float, threshold: float,
                      min_speech_duration_ms: float, min_silence_duration_ms: float, speech_pad_ms: float,
-                     max_speech_duration_s: float = 0.0, sample_rate: int = 16000) -> List[SpeechSegment]:
+                     max_speech_duration_s: float = 0.0, sample_rate: int = 16000, neg_threshold: Optional[float] = None) -> List[SpeechSegment]:
     """Frame probabilities -> speech regions with Silero-style hysteresis: onset at ``p >= threshold``;
-    an offset candidate opens at ``p < max(threshold - 0.15, 0.01)`` and is confirmed once that silence has
+    an offset candidate opens at ``p < neg_threshold`` (default ``max(threshold - 0.15, 0.01)``) and is confirmed once that silence has
     lasted ``min_silence`` frames; regions longer than ``max_speech`` are cut; regions shorter than
     ``min_speech`` are dropped; finally every region is padded by ``speech_pad`` without overlapping its
     neighbours."""
     n = len(probs)
     if n == 0:
         return []
-    off_thr = max(float(threshold) - 0.15, 0.01)
+    off_thr = float(neg_threshold) if neg_threshold is not None else max(float(threshold) - 0.15, 0.01)
     min_speech = max(1, int(min_speech_duration_ms / frame_ms))
     min_silence = max(1, int(min_silence_duration_ms / frame_ms))
     pad = max(0, int(speech_pad_ms / frame_ms))

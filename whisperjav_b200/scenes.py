@@ -235,9 +235,15 @@ class Scene:
 EnergyFn = Callable[[Sequence[Tuple[int, int]], int], List[np.ndarray]]
 
 
-def two_pass(cfg: SceneConfig, n_samples: int, sr: int, energy: EnergyFn) -> Tuple[List[Scene], List[Tuple[float, float]], Dict[str, int]]:
+FineFn = Callable[[List[Tuple[int, int, int]]], Dict[int, List[Tuple[float, float]]]]
+
+
+def two_pass(cfg: SceneConfig, n_samples: int, sr: int, energy: EnergyFn, fine_split: Optional[FineFn] = None
+             ) -> Tuple[List[Scene], List[Tuple[float, float]], Dict[str, int]]:
     """The driver of auditok_backend.py:229-524 on top of an energy provider ``energy(regions [(start, len)], window) -> per-region
-    uint64 sums of squares`` (the GPU kernel in the product, a numpy twin in the CPU tests).  Two provider calls in total."""
+    uint64 sums of squares`` (the GPU kernel in the product, a numpy twin in the CPU tests).  Two provider calls in total.
+    ``fine_split([(story line, first sample, end sample)]) -> {story line: [(start, end)] seconds relative to it}`` replaces the
+    energy pass 2 (the Silero-style detector, silero_backend.py:188-271)."""
     total = n_samples / sr
     window = int(ANALYSIS_WINDOW_S * sr)
     if window <= 0:
@@ -256,7 +262,11 @@ def two_pass(cfg: SceneConfig, n_samples: int, sr: int, energy: EnergyFn) -> Tup
                          cfg.pass1_energy_threshold)
     big = [(k, int(rs * sr), int(re_ * sr)) for k, (rs, re_) in enumerate(story) if not (cfg.min_duration <= re_ - rs <= cfg.max_duration)]
     fine: Dict[int, List[Tuple[float, float]]] = {}
-    if big:
+    if big and fine_split is not None:
+        fine = dict(fine_split(big))
+        for (k, _, _) in big:
+            fine.setdefault(k, [])
+    elif big:
         sums = energy([(a, b - a) for (_, a, b) in big], window)
         for (k, a, b), ss in zip(big, sums):
             dur = story[k][1] - story[k][0]
@@ -379,6 +389,128 @@ class B200SceneDetector:
 
 
 @dataclass
+class SileroSceneConfig(SceneConfig):
+    """Field for field ``SileroSceneConfig`` (silero_backend.py:27-49)."""
+    silero_threshold: float = 0.06
+    silero_neg_threshold: float = 0.15
+    silero_min_silence_ms: int = 1500
+    silero_min_speech_ms: int = 100
+    silero_max_speech_s: float = 600.0
+    silero_min_silence_at_max: int = 500
+    silero_speech_pad_ms: int = 200
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.assist_processing = False
+
+
+def silero_config_from_kwargs(kw: dict) -> SileroSceneConfig:
+    """silero_backend.py:97-149: the auditok fields from the legacy kwargs, but ``max_duration`` defaults to 420 s, ``pass2_max_duration``
+    is re-derived from it unless given, the brute-force chunk stays at 29 s."""
+    base = config_from_kwargs(kw)
+    user_p2 = "pass2_max_duration_s" in kw or "pass2_max_duration" in kw
+    return SileroSceneConfig(
+        max_duration=float(kw.get("max_duration_s", kw.get("max_duration", 420.0))), min_duration=base.min_duration,
+        pass1_min_duration=base.pass1_min_duration, pass1_max_duration=base.pass1_max_duration, pass1_max_silence=base.pass1_max_silence,
+        pass1_energy_threshold=base.pass1_energy_threshold, pass2_min_duration=base.pass2_min_duration,
+        pass2_max_duration=base.pass2_max_duration if user_p2 else None, pass2_max_silence=base.pass2_max_silence,
+        pass2_energy_threshold=base.pass2_energy_threshold, brute_force_fallback=base.brute_force_fallback,
+        brute_force_chunk_s=float(kw.get("brute_force_chunk_s", 29.0)), pad_edges_s=base.pad_edges_s, verbose_summary=base.verbose_summary,
+        force_mono=base.force_mono,
+        silero_threshold=float(kw.get("silero_threshold", 0.06)), silero_neg_threshold=float(kw.get("silero_neg_threshold", 0.15)),
+        silero_min_silence_ms=int(kw.get("silero_min_silence_ms", 1500)), silero_min_speech_ms=int(kw.get("silero_min_speech_ms", 100)),
+        silero_max_speech_s=float(kw.get("silero_max_speech_s", 600.0)), silero_min_silence_at_max=int(kw.get("silero_min_silence_at_max", 500)),
+        silero_speech_pad_ms=int(kw.get("silero_speech_pad_ms", 200)))
+
+
+class B200SileroSceneDetector(B200SceneDetector):
+    """``SileroSceneDetector`` (silero_backend.py:52-299): pass 1 is the energy gate of the parent, pass 2 runs the Silero-class VAD
+    over every oversized chapter -- here all of them in ONE batch of the GPU gate (``vad.VadB200.probs``) -- and turns the per-window
+    probabilities into speech regions with the hysteresis of ``get_speech_timestamps`` (``hostlogic.probs_to_regions`` with the
+    explicit ``neg_threshold`` the reference passes; seconds rounded to 0.1 s as silero-vad's ``return_seconds=True`` does).  A chapter
+    in which the VAD finds nothing falls through to the brute-force split, as in the reference.  ``silero_min_silence_at_max`` is
+    accepted; the split of a region longer than ``silero_max_speech_s`` (600 s by default) cuts at the limit.  The VAD network itself is
+    the Silero-class stack of ``vad.py`` (weights not available offline -- unpinned)."""
+
+    def __init__(self, config: Optional[SileroSceneConfig] = None, device: str = "cuda", vad=None, **kwargs: Any):
+        cfg = config if config is not None else silero_config_from_kwargs(kwargs)
+        super().__init__(config=cfg, device=device)
+        self._silero_config = cfg
+        self._vad = vad               # anything with ``probs(audio [B, S] device fp32, n_samples [B] device int32) -> [B, windows]``
+        self._vad_segments: List[Dict[str, float]] = []
+
+    @property
+    def name(self) -> str:
+        return "b200-silero"
+
+    @property
+    def display_name(self) -> str:
+        return "B200 Silero-style (energy pass 1 + CUDA VAD pass 2)"
+
+    def _region_probs(self, clips: List[np.ndarray]) -> List[np.ndarray]:
+        import torch
+        from .vad import WINDOW, VadB200
+        if self._vad is None:
+            self._vad = VadB200(device=self._device)
+        S = max(max(len(c) for c in clips), WINDOW)
+        host = torch.zeros(len(clips), S, dtype=torch.float32)
+        for i, c in enumerate(clips):
+            host[i, : len(c)] = torch.from_numpy(np.ascontiguousarray(c, dtype=np.float32))
+        ns = torch.tensor([len(c) for c in clips], dtype=torch.int32)
+        dev = getattr(self._vad, "device", "cpu")
+        probs = self._vad.probs(host.to(dev), ns.to(dev)).cpu().numpy()
+        return [probs[i, : (len(c) + WINDOW - 1) // WINDOW] for i, c in enumerate(clips)]
+
+    def _fine_split(self, audio: np.ndarray, sr: int) -> FineFn:
+        from . import hostlogic as H
+        from .vad import WINDOW
+        cfg = self._silero_config
+
+        def fine(big):
+            clips = []
+            for (_, a, b) in big:
+                x = np.asarray(audio[a:b], dtype=np.float32)
+                if sr != 16000:  # nearest-index decimation (backends/silero.py:411-414); the hot path hands 16 kHz audio
+                    x = x[np.linspace(0, len(x) - 1, int(len(x) * 16000 / sr)).astype(int)] if len(x) else x
+                clips.append(x)
+            out: Dict[int, List[Tuple[float, float]]] = {}
+            for (k, a, _), c, p in zip(big, clips, self._region_probs(clips) if clips else []):
+                dur = len(c) / 16000.0
+                regs = H.probs_to_regions(p, dur, frame_ms=1000.0 * WINDOW / 16000, threshold=cfg.silero_threshold,
+                                          neg_threshold=cfg.silero_neg_threshold, min_speech_duration_ms=cfg.silero_min_speech_ms,
+                                          min_silence_duration_ms=cfg.silero_min_silence_ms, speech_pad_ms=cfg.silero_speech_pad_ms,
+                                          max_speech_duration_s=cfg.silero_max_speech_s)
+                subs = [(max(round(r.start_sample / 16000.0, 1), 0), min(round(r.end_sample / 16000.0, 1), dur)) for r in regs]
+                out[k] = subs
+                t0 = a / sr
+                self._vad_segments.extend({"start_sec": round(t0 + s0, 3), "end_sec": round(t0 + s1, 3)} for s0, s1 in subs)
+            return out
+
+        return fine
+
+    def detect(self, audio, sample_rate: int = 16000):
+        import torch
+        self._vad_segments = []
+        host = audio.detach().cpu().numpy() if isinstance(audio, torch.Tensor) else np.asarray(audio, dtype=np.float32)
+        return two_pass(self._config, int(host.shape[0]), int(sample_rate), self._energy_provider(audio), self._fine_split(host, int(sample_rate)))
+
+    def detect_scenes(self, audio_path: Path, output_dir: Path, media_basename: str, **kwargs: Any):
+        res = super().detect_scenes(audio_path, output_dir, media_basename, **kwargs)
+        cfg = self._silero_config
+        res.parameters.update({"silero_threshold": cfg.silero_threshold, "silero_neg_threshold": cfg.silero_neg_threshold,
+                               "silero_min_silence_ms": cfg.silero_min_silence_ms, "silero_min_speech_ms": cfg.silero_min_speech_ms,
+                               "silero_max_speech_s": cfg.silero_max_speech_s, "silero_speech_pad_ms": cfg.silero_speech_pad_ms})
+        if hasattr(res, "vad_segments"):
+            res.vad_segments = self._vad_segments or None
+        return res
+
+    def cleanup(self) -> None:
+        super().cleanup()
+        self._vad = None
+        self._vad_segments = []
+
+
+@dataclass
 class _Result:
     """``SceneDetectionResult`` (base.py:100-183) when WhisperJAV is not importable."""
     scenes: List[Scene]
@@ -387,6 +519,7 @@ class _Result:
     parameters: Dict[str, Any] = field(default_factory=dict)
     processing_time_sec: float = 0.0
     coarse_boundaries: Optional[List[Dict[str, Any]]] = None
+    vad_segments: Optional[List[Dict[str, Any]]] = None
 
     @property
     def num_scenes(self) -> int:
